@@ -1,0 +1,146 @@
+/* libnzcp_prover.so -- C ABI of the B200-native Groth16 (BN254) prover for the NZCP circuit.
+ *
+ * This is the drop-in boundary for the one hot path of noway/nzcp-circom: snarkjs `groth16.prove(zkey, wtns)`
+ * (and the `groth16.fullProve` wrapper around it).  The reference tree pins snarkjs ^0.4.12 in
+ * /root/reference/package.json:12 (resolved 0.4.12 at yarn.lock:987-999; arithmetic in ffjavascript 0.2.48,
+ * yarn.lock:408-416; WASM kernels in wasmcurves 0.1.0, yarn.lock:1132-1135); the artefacts these calls exchange are
+ * the `.zkey` / `.wtns` files ignored at /root/reference/.gitignore:2-4.  A Node N-API addon (or Python ctypes,
+ * see INTEGRATION.md) binds these entry points 1:1.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative NZCP_E_* code and
+ * never throws across the boundary; `nzcp_last_error()` returns a thread-local message for the last failure.
+ * All field elements crossing the ABI are 32-byte little-endian integers.  A handle may be used by one thread at a
+ * time; the library owns all device memory.  There is NO CPU fallback: without a CUDA device every compute entry
+ * point fails with NZCP_E_CUDA.
+ */
+#ifndef NZCP_PROVER_H
+#define NZCP_PROVER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NZCP_OK 0
+#define NZCP_E_ARG (-1)        /* null pointer / bad size / bad option */
+#define NZCP_E_FORMAT (-2)     /* malformed .zkey / .wtns container */
+#define NZCP_E_NOT_GROTH16 (-3)/* snarkjs: "zkey file is not groth16" */
+#define NZCP_E_CURVE (-4)      /* snarkjs: "Curve of the witness does not match the curve of the proving key" */
+#define NZCP_E_WITNESS_LEN (-5)/* snarkjs: "Invalid witness length. Circuit: X, witness: Y" */
+#define NZCP_E_CUDA (-6)       /* CUDA runtime failure (incl. no device) */
+#define NZCP_E_RANGE (-7)      /* a witness value is not a canonical field element */
+#define NZCP_E_INTERNAL (-8)
+
+typedef struct nzcp_zkey nzcp_zkey;     /* proving key resident on one GPU (replaces the per-call readSection()s of */
+                                        /* snarkjs groth16_prove.js: sections 4-9 are parsed and uploaded once)     */
+typedef struct nzcp_prover nzcp_prover; /* per-stream work buffers for one in-flight proof                          */
+
+/* zkey section 2 header as snarkjs zkey_utils.js readHeader() returns it (coordinates plain, not Montgomery). */
+typedef struct nzcp_zkey_info {
+  uint32_t n_vars;
+  uint32_t n_public;
+  uint32_t domain_size;
+  uint32_t power;
+  uint64_t n_coefs;
+  uint8_t alpha1[64], beta1[64], delta1[64];     /* G1: x, y                      */
+  uint8_t beta2[128], gamma2[128], delta2[128];  /* G2: x.c0, x.c1, y.c0, y.c1    */
+  uint64_t device_bytes;
+} nzcp_zkey_info;
+
+/* The proof: 8 plain 32-byte LE values  A.x A.y | B.x.c0 B.x.c1 B.y.c0 B.y.c1 | C.x C.y
+ * (snarkjs proof.pi_a / pi_b / pi_c before stringification; a point at infinity is all zero). */
+typedef struct nzcp_proof {
+  uint8_t pi_a[64];
+  uint8_t pi_b[128];
+  uint8_t pi_c[64];
+} nzcp_proof;
+
+/* Intermediate results the parity tests compare bit-for-bit against the oracle (north_star: "H coefficients, each
+ * MSM result and the final proof").  Affine, plain, same coordinate order as nzcp_proof. */
+typedef struct nzcp_prove_debug {
+  uint8_t msm_a[64];
+  uint8_t msm_b1[64];
+  uint8_t msm_b2[128];
+  uint8_t msm_c[64];
+  uint8_t msm_h[64];
+  uint8_t* h_scalars;      /* optional: caller buffer of domain_size*32 bytes receiving the joinABC output, or NULL */
+  float stage_ms[8];       /* device time: 0 upload, 1 r1cs eval, 2 ntt pipeline+join, 3 msm A, 4 msm B1, 5 msm B2, */
+                           /*              6 msm C, 7 msm H                                                         */
+} nzcp_prove_debug;
+
+const char* nzcp_last_error(void);
+int nzcp_device_count(void);
+
+/* Parse a snarkjs .zkey held in host memory and upload it to `device`.  Caller keeps ownership of `bytes`. */
+int nzcp_zkey_load(const uint8_t* bytes, size_t len, int device, nzcp_zkey** out);
+int nzcp_zkey_info_get(const nzcp_zkey* zk, nzcp_zkey_info* info);
+void nzcp_zkey_free(nzcp_zkey* zk);
+
+/* Work buffers + streams for proofs against `zk`.  Several provers may share one zkey (one per host thread). */
+int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out);
+void nzcp_prover_free(nzcp_prover* p);
+
+/* groth16.prove: `wtns` is a complete .wtns file image.  r, s: 32-byte LE blinding scalars (< r); NULL draws them
+ * from the OS CSPRNG as snarkjs's Fr.random() does.  `dbg` may be NULL. */
+int nzcp_prove(nzcp_prover* p, const uint8_t* wtns, size_t wtns_len, const uint8_t* r, const uint8_t* s,
+               nzcp_proof* proof, nzcp_prove_debug* dbg);
+/* Same, but the witness is a bare array of n_vars 32-byte LE values (section 2 of a .wtns). */
+int nzcp_prove_witness(nzcp_prover* p, const uint8_t* witness, uint32_t n_witness, const uint8_t* r, const uint8_t* s,
+                       nzcp_proof* proof, nzcp_prove_debug* dbg);
+/* Device-resident variant used for kernel-only timing: witness already in HBM (device pointer, n_vars * 32 B). */
+int nzcp_prove_device(nzcp_prover* p, const void* d_witness, const uint8_t* r, const uint8_t* s, nzcp_proof* proof,
+                      nzcp_prove_debug* dbg);
+/* Device pointer of the prover's own witness buffer (n_vars * 32 B), for callers that fill it themselves. */
+void* nzcp_prover_witness_buffer(nzcp_prover* p);
+/* Number of kernel launches issued by this prover so far. */
+uint64_t nzcp_prover_launch_count(const nzcp_prover* p);
+
+/* ---- standalone kernels (BASELINE config 4: NTT + MSM sweeps; also the fine-grained parity tests) ---- */
+/* Natural-order NTT / iNTT over Fr of 2^log_n Montgomery-form elements in host memory (snarkjs Fr.fft / Fr.ifft). */
+int nzcp_ntt(uint8_t* data, int log_n, int inverse, int device, float* kernel_ms);
+/* The prover's H pipeline on `batch` polynomials: evaluations on the subgroup -> evaluations on the odd coset. */
+int nzcp_ntt_coset(uint8_t* data, int log_n, int batch, int device, float* kernel_ms);
+/* MSM over G1 (g2 = 0, 64-byte bases) or G2 (g2 = 1, 128-byte bases): Montgomery affine bases as in the zkey, plain
+ * scalars.  window_bits = 0 picks the default.  out = plain affine point (64 / 128 bytes). */
+int nzcp_msm(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int g2, int window_bits, int device,
+             uint8_t* out, float* kernel_ms);
+/* Device self-test of the field / curve arithmetic against the host build of the same code; returns the number of
+ * mismatches in *n_bad (0 = pass). */
+int nzcp_selftest(int device, uint64_t seed, uint32_t n_cases, uint32_t* n_bad);
+/* Element-wise Fr/Fq ops on the device, for limb-exact parity tests: op 0 mul, 1 add, 2 sub (Montgomery-form in/out),
+ * field 0 = Fr, 1 = Fq. */
+int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int device);
+
+/* ---- host hooks: the library's __host__ __device__ arithmetic compiled for the CPU (what the O(1) host glue runs).
+ * Test-only; they let the no-GPU suite pin that code against the oracle.  op: 0 mul, 1 add, 2 sub. */
+int nzcp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+/* k * base (Montgomery affine base as in the zkey, NULL = the group generator); out = plain affine. */
+int nzcp_host_scalar_mul(int g2, const uint8_t* base_mont, const uint8_t* scalar, uint8_t* out_plain);
+/* Fr.w[k] of ffjavascript (plain form). */
+int nzcp_host_root_of_unity(int k, uint8_t* out_plain);
+
+/* ---- synthetic circuits of the NZCP shape (no circom / snarkjs in this environment) ---- */
+typedef struct nzcp_synth nzcp_synth;
+/* Random forward-solvable R1CS: n_constraints constraints, n_public public outputs, n_free free inputs, each
+ * constraint defines one fresh wire.  Wire value classes (bits / bytes / full-width) follow SURVEY.md 8d. */
+int nzcp_synth_create(uint64_t seed, uint32_t n_constraints, uint32_t n_public, uint32_t n_free, nzcp_synth** out);
+void nzcp_synth_free(nzcp_synth* c);
+int nzcp_synth_dims(const nzcp_synth* c, uint32_t* n_vars, uint32_t* n_constraints, uint32_t* n_public,
+                    uint32_t* domain_size, uint64_t* n_coefs);
+/* Size in bytes of the .zkey / .r1cs / .wtns images the writers below produce. */
+size_t nzcp_synth_zkey_size(const nzcp_synth* c);
+size_t nzcp_synth_r1cs_size(const nzcp_synth* c);
+size_t nzcp_synth_wtns_size(const nzcp_synth* c);
+/* Groth16 setup from explicit toxic waste (5 x 32-byte LE: tau, alpha, beta, gamma, delta) -> snarkjs-format .zkey.
+ * The fixed-base scalar multiplications run on `device`. */
+int nzcp_synth_write_zkey(const nzcp_synth* c, const uint8_t toxic[160], int device, uint8_t* out, size_t cap);
+int nzcp_synth_write_r1cs(const nzcp_synth* c, uint8_t* out, size_t cap);
+/* Satisfying witness for the given seed -> .wtns image. */
+int nzcp_synth_write_wtns(const nzcp_synth* c, uint64_t witness_seed, uint8_t* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NZCP_PROVER_H */

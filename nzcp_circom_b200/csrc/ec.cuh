@@ -1,0 +1,205 @@
+// BN254 G1 (over Fq) and G2 (over Fq2 = Fq[u]/(u^2+1)) group arithmetic, templated over the coordinate field.
+//
+// Replaces (upstream, not vendored: yarn.lock:408-416, 1132-1135) ffjavascript src/f2field.js + src/ec.js and
+// wasmcurves build_curve_jacobian_a0.js (g1m_* / g2m_* add, double, affine conversion).  The WASM code works in
+// Jacobian coordinates; here bucket accumulators are extended-Jacobian "XYZZ" (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2)
+// because the mixed addition is 8M+2S and needs no inversion.  Group elements are exact, so the affine result
+// of any sum is bit-identical to the reference's whatever coordinate system produced it.
+//
+// Affine buffers follow the zkey convention: Montgomery coordinates, (0,0) = point at infinity.
+#pragma once
+#include "fp.cuh"
+
+namespace nzcp {
+
+// ------------------------------------------------------------------------------------------------ Fq2
+struct Fq2 {
+  Fq c0, c1;
+  HD static Fq2 zero() { return Fq2{Fq::zero(), Fq::zero()}; }
+  HD static Fq2 one() { return Fq2{Fq::one(), Fq::zero()}; }
+  HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+  HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+};
+
+// uniform free-function interface over Fq and Fq2
+HD Fq f_add(const Fq& a, const Fq& b) { return fp_add(a, b); }
+HD Fq f_sub(const Fq& a, const Fq& b) { return fp_sub(a, b); }
+HD Fq f_mul(const Fq& a, const Fq& b) { return fp_mul(a, b); }
+HD Fq f_sqr(const Fq& a) { return fp_sqr(a); }
+HD Fq f_neg(const Fq& a) { return fp_neg(a); }
+HD Fq f_dbl(const Fq& a) { return fp_add(a, a); }
+HDN inline Fq f_inv(const Fq& a) { return fp_inv(a); }
+HD Fq f_from_mont(const Fq& a) { return fp_from_mont(a); }
+
+HD Fq2 f_add(const Fq2& a, const Fq2& b) { return Fq2{fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
+HD Fq2 f_sub(const Fq2& a, const Fq2& b) { return Fq2{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
+HD Fq2 f_neg(const Fq2& a) { return Fq2{fp_neg(a.c0), fp_neg(a.c1)}; }
+HD Fq2 f_dbl(const Fq2& a) { return Fq2{fp_add(a.c0, a.c0), fp_add(a.c1, a.c1)}; }
+HD Fq2 f_mul(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 Fq mul; u^2 = -1
+  Fq t0 = fp_mul(a.c0, b.c0);
+  Fq t1 = fp_mul(a.c1, b.c1);
+  Fq t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+  return Fq2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
+}
+HD Fq2 f_sqr(const Fq2& a) {  // (c0+c1)(c0-c1) + 2 c0 c1 u : 2 Fq mul
+  Fq t0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
+  Fq t1 = fp_mul(a.c0, a.c1);
+  return Fq2{t0, fp_add(t1, t1)};
+}
+HDN inline Fq2 f_inv(const Fq2& a) {
+  Fq d = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+  return Fq2{fp_mul(a.c0, d), fp_neg(fp_mul(a.c1, d))};
+}
+HD Fq2 f_from_mont(const Fq2& a) { return Fq2{fp_from_mont(a.c0), fp_from_mont(a.c1)}; }
+
+// ------------------------------------------------------------------------------------------------ points
+template <class F>
+struct Affine {
+  F x, y;
+  HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+  HD static Affine inf() { return Affine{F::zero(), F::zero()}; }
+};
+
+template <class F>
+struct XYZZ {
+  F x, y, zz, zzz;
+  HD bool is_inf() const { return zz.is_zero(); }
+  HD static XYZZ inf() { return XYZZ{F::zero(), F::zero(), F::zero(), F::zero()}; }
+  HD static XYZZ from_affine(const Affine<F>& p) {
+    if (p.is_inf()) return inf();
+    return XYZZ{p.x, p.y, F::one(), F::one()};
+  }
+};
+
+template <class F>
+HD XYZZ<F> xyzz_neg(const XYZZ<F>& p) {
+  return XYZZ<F>{p.x, f_neg(p.y), p.zz, p.zzz};
+}
+
+// dbl-2008-s-1 (a = 0)
+template <class F>
+HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
+  if (p.is_inf()) return p;
+  F u = f_dbl(p.y);
+  F v = f_sqr(u);
+  F w = f_mul(u, v);
+  F s = f_mul(p.x, v);
+  F xx = f_sqr(p.x);
+  F m = f_add(f_dbl(xx), xx);
+  XYZZ<F> r;
+  r.x = f_sub(f_sqr(m), f_dbl(s));
+  r.y = f_sub(f_mul(m, f_sub(s, r.x)), f_mul(w, p.y));
+  r.zz = f_mul(v, p.zz);
+  r.zzz = f_mul(w, p.zzz);
+  return r;
+}
+
+// Doubling of an affine point (mdbl-2008-s-1); y != 0 on these curves (no 2-torsion).
+template <class F>
+HD XYZZ<F> xyzz_dbl_affine(const Affine<F>& p) {
+  F u = f_dbl(p.y);
+  F v = f_sqr(u);
+  F w = f_mul(u, v);
+  F s = f_mul(p.x, v);
+  F xx = f_sqr(p.x);
+  F m = f_add(f_dbl(xx), xx);
+  XYZZ<F> r;
+  r.x = f_sub(f_sqr(m), f_dbl(s));
+  r.y = f_sub(f_mul(m, f_sub(s, r.x)), f_mul(w, p.y));
+  r.zz = v;
+  r.zzz = w;
+  return r;
+}
+
+// acc += (q.x, neg ? -q.y : q.y)   madd-2008-s, 8M + 2S; q must not be infinity.
+template <class F>
+HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q, bool neg) {
+  F qy = neg ? f_neg(q.y) : q.y;
+  if (acc.is_inf()) {
+    acc.x = q.x;
+    acc.y = qy;
+    acc.zz = F::one();
+    acc.zzz = F::one();
+    return;
+  }
+  F u2 = f_mul(q.x, acc.zz);
+  F s2 = f_mul(qy, acc.zzz);
+  F p = f_sub(u2, acc.x);
+  F r = f_sub(s2, acc.y);
+  if (p.is_zero()) {
+    if (r.is_zero()) {
+      acc = xyzz_dbl_affine(Affine<F>{q.x, qy});
+    } else {
+      acc = XYZZ<F>::inf();
+    }
+    return;
+  }
+  F pp = f_sqr(p);
+  F ppp = f_mul(p, pp);
+  F qq = f_mul(acc.x, pp);
+  F x3 = f_sub(f_sub(f_sqr(r), ppp), f_dbl(qq));
+  acc.y = f_sub(f_mul(r, f_sub(qq, x3)), f_mul(acc.y, ppp));
+  acc.x = x3;
+  acc.zz = f_mul(acc.zz, pp);
+  acc.zzz = f_mul(acc.zzz, ppp);
+}
+
+// acc += b   add-2008-s, 12M + 2S
+template <class F>
+HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
+  if (b.is_inf()) return;
+  if (acc.is_inf()) {
+    acc = b;
+    return;
+  }
+  F u1 = f_mul(acc.x, b.zz);
+  F u2 = f_mul(b.x, acc.zz);
+  F s1 = f_mul(acc.y, b.zzz);
+  F s2 = f_mul(b.y, acc.zzz);
+  F p = f_sub(u2, u1);
+  F r = f_sub(s2, s1);
+  if (p.is_zero()) {
+    if (r.is_zero()) {
+      acc = xyzz_dbl(acc);
+    } else {
+      acc = XYZZ<F>::inf();
+    }
+    return;
+  }
+  F pp = f_sqr(p);
+  F ppp = f_mul(p, pp);
+  F qq = f_mul(u1, pp);
+  F x3 = f_sub(f_sub(f_sqr(r), ppp), f_dbl(qq));
+  acc.y = f_sub(f_mul(r, f_sub(qq, x3)), f_mul(s1, ppp));
+  acc.x = x3;
+  acc.zz = f_mul(f_mul(acc.zz, b.zz), pp);
+  acc.zzz = f_mul(f_mul(acc.zzz, b.zzz), ppp);
+}
+
+// k * p, k = plain 256-bit little-endian scalar (8 limbs); left-to-right double-and-add.
+template <class F>
+HDN inline XYZZ<F> xyzz_mul(const XYZZ<F>& p, const uint32_t* k) {
+  XYZZ<F> r = XYZZ<F>::inf();
+  for (int i = 255; i >= 0; i--) {
+    r = xyzz_dbl(r);
+    if ((k[i >> 5] >> (i & 31)) & 1) xyzz_add(r, p);
+  }
+  return r;
+}
+
+// Montgomery-form affine; infinity -> (0,0).
+template <class F>
+HDN inline Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
+  if (p.is_inf()) return Affine<F>::inf();
+  F iz3 = f_inv(p.zzz);               // 1/Z^3
+  F iz2 = f_sqr(f_mul(iz3, p.zz));    // (Z^2/Z^3)^2 = 1/Z^2
+  return Affine<F>{f_mul(p.x, iz2), f_mul(p.y, iz3)};
+}
+
+typedef Affine<Fq> G1Affine;
+typedef Affine<Fq2> G2Affine;
+typedef XYZZ<Fq> G1XYZZ;
+typedef XYZZ<Fq2> G2XYZZ;
+
+}  // namespace nzcp

@@ -1,0 +1,478 @@
+// BN254 prime fields Fr / Fq: 254-bit Montgomery arithmetic on 8 x 32-bit limbs, R = 2^256.
+//
+// Replaces (upstream, not vendored in /root/reference -- see package.json:12, yarn.lock:408-416,1132-1135)
+// wasmcurves 0.1.0 build_f1m.js (f1m_mul / f1m_add / f1m_sub / f1m_toMontgomery / f1m_fromMontgomery), which
+// snarkjs reaches through ffjavascript's Fr / F1 objects.  Same representation contract as the WASM code:
+// values are canonical (< p), Montgomery form is x*R mod p, buffers are little-endian.
+//
+// Every function is __host__ __device__: the host build (g++ via nvcc) is what the CPU-side unit tests and
+// the O(1) host glue (twiddle tables, proof finalisation) run; the device build swaps in IMAD carry-chain
+// PTX for mul/add/sub (sm_100a: mad.lo.cc/madc.hi.cc pairs fuse to IMAD.WIDE.U32 + carry predicates).
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#define HDN __host__ __device__
+#else
+#define HD inline
+#define HDN
+#endif
+
+#ifndef NZCP_MUL_PTX
+#define NZCP_MUL_PTX 1
+#endif
+
+namespace nzcp {
+
+struct FrParams {
+  HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  HD static constexpr uint32_t one(int i) {  // R mod r
+    constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  HD static constexpr uint32_t r2(int i) {  // R^2 mod r
+    constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return m[i];
+  }
+  static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32
+};
+
+struct FqParams {
+  HD static constexpr uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  HD static constexpr uint32_t one(int i) {  // R mod q
+    constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  HD static constexpr uint32_t r2(int i) {  // R^2 mod q
+    constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return m[i];
+  }
+  static constexpr uint32_t INV = 0xe4866389u;  // -q^-1 mod 2^32
+};
+
+template <class P>
+struct alignas(16) Fp {
+  uint32_t v[8];
+
+  HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  HD static Fp one() {  // Montgomery form of 1
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  HD static Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::r2(i);
+    return r;
+  }
+  HD static Fp modulus() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::mod(i);
+    return r;
+  }
+  HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i];
+    return o == 0;
+  }
+  HD bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// ------------------------------------------------------------------------------------------ portable core
+template <class P>
+HD bool fp_geq_mod(const uint32_t* t) {  // t >= p ?
+#pragma unroll
+  for (int i = 7; i >= 0; i--) {
+    if (t[i] > P::mod(i)) return true;
+    if (t[i] < P::mod(i)) return false;
+  }
+  return true;
+}
+
+template <class P>
+HD Fp<P> fp_add_portable(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[8], u[8];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] + b.v[i];
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  // p < 2^254 so a+b < 2^255: no carry out of limb 7.
+  int64_t bw = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    bw += (int64_t)t[i] - (int64_t)P::mod(i);
+    u[i] = (uint32_t)bw;
+    bw >>= 32;
+  }
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = bw ? t[i] : u[i];
+  return r;
+}
+
+template <class P>
+HD Fp<P> fp_sub_portable(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[8];
+  int64_t bw = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    bw += (int64_t)a.v[i] - (int64_t)b.v[i];
+    t[i] = (uint32_t)bw;
+    bw >>= 32;
+  }
+  uint32_t mask = bw ? 0xffffffffu : 0u;
+  uint64_t c = 0;
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)t[i] + (P::mod(i) & mask);
+    r.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  return r;
+}
+
+// CIOS Montgomery product, 32-bit digits, 64-bit accumulators.  a, b < p  ->  a*b/R mod p, canonical.
+template <class P>
+HD Fp<P> fp_mul_portable(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)a.v[j] * b.v[i] + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[8] = (uint32_t)c;  // p < 2^254: never needs a 10th limb
+    uint32_t m = t[0] * P::INV;
+    c = ((uint64_t)m * P::mod(0) + t[0]) >> 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      c += (uint64_t)m * P::mod(j) + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[7] = (uint32_t)c;
+    t[8] = (uint32_t)(c >> 32);
+  }
+  Fp<P> r;
+  if (fp_geq_mod<P>(t)) {
+    int64_t bw = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      bw += (int64_t)t[i] - (int64_t)P::mod(i);
+      r.v[i] = (uint32_t)bw;
+      bw >>= 32;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------ device PTX core
+#if defined(__CUDA_ARCH__)
+// r = (t >= p) ? t - p : t, branch-free.
+template <class P>
+__device__ __forceinline__ void fp_final_sub(uint32_t* t) {
+  uint32_t u[8], bw;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(bw)
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+        "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)), "r"(P::mod(5)),
+        "r"(P::mod(6)), "r"(P::mod(7)));
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = bw ? t[i] : u[i];
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> fp_add_ptx(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[8];
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  fp_final_sub<P>(t);
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> fp_sub_ptx(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t[8], bw;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(bw)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  Fp<P> r;
+  // bw = 0xffffffff when a < b: add p back.
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+        "=r"(r.v[7])
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+        "r"(P::mod(0) & bw), "r"(P::mod(1) & bw), "r"(P::mod(2) & bw), "r"(P::mod(3) & bw), "r"(P::mod(4) & bw),
+        "r"(P::mod(5) & bw), "r"(P::mod(6) & bw), "r"(P::mod(7) & bw));
+  return r;
+}
+
+// One row of the product: (ev, od) hold T = ev + od * 2^32 (od is offset by one limb).
+//   first row : od = (a1,a3,a5,a7)*bi ; ev = (a0,a2,a4,a6)*bi
+//   other rows: T was divided by 2^32 by the previous reduction, so the arrays swap roles; the old even array
+//               (now `od`) is consumed two limbs ahead (od[j+2]) and its stray limb od[1] lands in ev[0].
+template <bool FIRST>
+__device__ __forceinline__ void fp_mad_row(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi) {
+  if (FIRST) {
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(od[0]), "=r"(od[1]), "=r"(od[2]), "=r"(od[3]), "=r"(od[4]), "=r"(od[5]), "=r"(od[6]), "=r"(od[7])
+        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(ev[0]), "=r"(ev[1]), "=r"(ev[2]), "=r"(ev[3]), "=r"(ev[4]), "=r"(ev[5]), "=r"(ev[6]), "=r"(ev[7])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+  } else {
+    asm("add.cc.u32 %0, %0, %9;\n\t"          // ev0 += od1 (stray limb), carry continues into od chain
+        "madc.lo.cc.u32 %8, %16, %24, %10;\n\t"   // od0 = lo(a1*bi) + od2
+        "madc.hi.cc.u32 %9, %16, %24, %11;\n\t"   // od1 = hi(a1*bi) + od3
+        "madc.lo.cc.u32 %10, %17, %24, %12;\n\t"  // od2 = lo(a3*bi) + od4
+        "madc.hi.cc.u32 %11, %17, %24, %13;\n\t"  // od3 = hi(a3*bi) + od5
+        "madc.lo.cc.u32 %12, %18, %24, %14;\n\t"  // od4 = lo(a5*bi) + od6
+        "madc.hi.cc.u32 %13, %18, %24, %15;\n\t"  // od5 = hi(a5*bi) + od7
+        "madc.lo.cc.u32 %14, %19, %24, 0;\n\t"    // od6 = lo(a7*bi)
+        "madc.hi.u32 %15, %19, %24, 0;\n\t"       // od7 = hi(a7*bi) + carry
+        "mad.lo.cc.u32 %0, %20, %24, %0;\n\t"     // ev += (a0,a2,a4,a6)*bi
+        "madc.hi.cc.u32 %1, %20, %24, %1;\n\t"
+        "madc.lo.cc.u32 %2, %21, %24, %2;\n\t"
+        "madc.hi.cc.u32 %3, %21, %24, %3;\n\t"
+        "madc.lo.cc.u32 %4, %22, %24, %4;\n\t"
+        "madc.hi.cc.u32 %5, %22, %24, %5;\n\t"
+        "madc.lo.cc.u32 %6, %23, %24, %6;\n\t"
+        "madc.hi.cc.u32 %7, %23, %24, %7;\n\t"
+        "addc.u32 %15, %15, 0;"                   // carry out of ev (limb 8) -> od7
+        : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+          "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+  }
+}
+
+// Montgomery reduction row: m = ev0 * INV; T += m * p  (makes ev0 == 0).
+template <class P>
+__device__ __forceinline__ void fp_redc_row(uint32_t* ev, uint32_t* od) {
+  uint32_t m = ev[0] * P::INV;
+  asm("mad.lo.cc.u32 %8, %16, %24, %8;\n\t"  // od += (p1,p3,p5,p7)*m
+      "madc.hi.cc.u32 %9, %16, %24, %9;\n\t"
+      "madc.lo.cc.u32 %10, %17, %24, %10;\n\t"
+      "madc.hi.cc.u32 %11, %17, %24, %11;\n\t"
+      "madc.lo.cc.u32 %12, %18, %24, %12;\n\t"
+      "madc.hi.cc.u32 %13, %18, %24, %13;\n\t"
+      "madc.lo.cc.u32 %14, %19, %24, %14;\n\t"
+      "madc.hi.u32 %15, %19, %24, %15;\n\t"   // top limbs of a and p are < 2^30: cannot carry out
+      "mad.lo.cc.u32 %0, %20, %24, %0;\n\t"   // ev += (p0,p2,p4,p6)*m
+      "madc.hi.cc.u32 %1, %20, %24, %1;\n\t"
+      "madc.lo.cc.u32 %2, %21, %24, %2;\n\t"
+      "madc.hi.cc.u32 %3, %21, %24, %3;\n\t"
+      "madc.lo.cc.u32 %4, %22, %24, %4;\n\t"
+      "madc.hi.cc.u32 %5, %22, %24, %5;\n\t"
+      "madc.lo.cc.u32 %6, %23, %24, %6;\n\t"
+      "madc.hi.cc.u32 %7, %23, %24, %7;\n\t"
+      "addc.u32 %15, %15, 0;"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]),
+        "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
+      : "r"(P::mod(1)), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)), "r"(P::mod(0)), "r"(P::mod(2)),
+        "r"(P::mod(4)), "r"(P::mod(6)), "r"(m));
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> fp_mul_ptx(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t ev[8], od[8];
+  fp_mad_row<true>(ev, od, a.v, b.v[0]);
+  fp_redc_row<P>(ev, od);
+  fp_mad_row<false>(od, ev, a.v, b.v[1]);
+  fp_redc_row<P>(od, ev);
+  fp_mad_row<false>(ev, od, a.v, b.v[2]);
+  fp_redc_row<P>(ev, od);
+  fp_mad_row<false>(od, ev, a.v, b.v[3]);
+  fp_redc_row<P>(od, ev);
+  fp_mad_row<false>(ev, od, a.v, b.v[4]);
+  fp_redc_row<P>(ev, od);
+  fp_mad_row<false>(od, ev, a.v, b.v[5]);
+  fp_redc_row<P>(od, ev);
+  fp_mad_row<false>(ev, od, a.v, b.v[6]);
+  fp_redc_row<P>(ev, od);
+  fp_mad_row<false>(od, ev, a.v, b.v[7]);
+  fp_redc_row<P>(od, ev);
+  // last row used (od, ev) as (even, odd): result = (od >> 32) + ev
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, 0;"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7])
+      : "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+  fp_final_sub<P>(ev);
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = ev[i];
+  return r;
+}
+#endif  // __CUDA_ARCH__
+
+// ------------------------------------------------------------------------------------------ public ops
+template <class P>
+HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && NZCP_MUL_PTX
+  return fp_add_ptx(a, b);
+#else
+  return fp_add_portable(a, b);
+#endif
+}
+template <class P>
+HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && NZCP_MUL_PTX
+  return fp_sub_ptx(a, b);
+#else
+  return fp_sub_portable(a, b);
+#endif
+}
+template <class P>
+HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && NZCP_MUL_PTX
+  return fp_mul_ptx(a, b);
+#else
+  return fp_mul_portable(a, b);
+#endif
+}
+template <class P>
+HD Fp<P> fp_sqr(const Fp<P>& a) {
+  return fp_mul(a, a);
+}
+template <class P>
+HD Fp<P> fp_neg(const Fp<P>& a) {
+  return a.is_zero() ? a : fp_sub(Fp<P>::modulus(), a);
+}
+template <class P>
+HD Fp<P> fp_dbl(const Fp<P>& a) {
+  return fp_add(a, a);
+}
+template <class P>
+HD Fp<P> fp_to_mont(const Fp<P>& a) {
+  return fp_mul(a, Fp<P>::r2());
+}
+template <class P>
+HD Fp<P> fp_from_mont(const Fp<P>& a) {
+  Fp<P> o = Fp<P>::zero();
+  o.v[0] = 1;
+  return fp_mul(a, o);
+}
+// a^e, e given as 8 little-endian limbs (plain integer).  a in Montgomery form.
+template <class P>
+HDN inline Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e) {
+  Fp<P> r = Fp<P>::one();
+  bool started = false;
+  for (int i = 255; i >= 0; i--) {
+    if (started) r = fp_sqr(r);
+    if ((e[i >> 5] >> (i & 31)) & 1) {
+      r = started ? fp_mul(r, a) : a;
+      started = true;
+    }
+  }
+  return r;
+}
+// Fermat inverse (a != 0), Montgomery in and out.
+template <class P>
+HDN inline Fp<P> fp_inv(const Fp<P>& a) {
+  uint32_t e[8];
+  for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+  e[0] -= 2;  // low limb of both moduli is > 2
+  return fp_pow(a, e);
+}
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+}  // namespace nzcp

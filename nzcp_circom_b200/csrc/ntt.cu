@@ -1,0 +1,314 @@
+// BN254-Fr number-theoretic transforms for the Groth16 H pipeline.
+//
+// Replaces (upstream, not vendored: yarn.lock:408-416, 1132-1135)
+//   ffjavascript src/engine_fft.js  (Fr.fft / Fr.ifft: natural order in and out, worker fan-out of <=2^14 blocks,
+//                                    frm_fft / frm_ifft / frm_fftJoin / frm_fftFinal in wasmcurves build_fft.js)
+//   ffjavascript src/engine_applykey.js (Fr.batchApplyKey(buf, 1, inc): element i *= inc^i)
+//   wasmcurves build_qap.js qap_joinABC + frm_batchFromMontgomery (joinABC in snarkjs src/groth16_prove.js)
+// as called from snarkjs groth16_prove.js:  for X in A,B,C: ifft -> batchApplyKey -> fft ; joinABC.
+//
+// B200 design.  One polynomial is n x 32 B (32 MiB at n = 2^20).  Per polynomial the pipeline is
+//     iNTT as decimation-in-frequency (natural in -> bit-reversed out)
+//     x  n^-1 * inc^bitrev(p)            (the 1/n of the iNTT fused with batchApplyKey, one table)
+//     NTT as decimation-in-time          (bit-reversed in -> natural out)
+// so no bit-reversal pass is ever materialised.  Stages are grouped into passes of <= 10 radix-2 stages that run
+// out of shared memory; the low DIF pass, the scale and the low DIT pass touch the same contiguous tile and are one
+// kernel.  At n = 2^20 that is 3 launches (hi DIF, fused lo, hi DIT) = 3 read+write sweeps of HBM per polynomial,
+// A/B/C batched through grid.y.  Shared tiles are limb-planar (8 planes of u32) with index padding l + l/32 so that
+// both unit-stride and stride-2 butterflies are bank-conflict free.
+#include "common.cuh"
+
+namespace nzcp {
+
+static constexpr int kNttThreads = 256;
+static constexpr int kMaxPassBits = 10;
+
+__device__ __forceinline__ uint32_t pad_idx(uint32_t l) { return l + (l >> 5); }
+
+__device__ __forceinline__ Fr sm_load(const uint32_t* sm, uint32_t plane, uint32_t l) {
+  Fr r;
+  uint32_t p = pad_idx(l);
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.v[k] = sm[k * plane + p];
+  return r;
+}
+__device__ __forceinline__ void sm_store(uint32_t* sm, uint32_t plane, uint32_t l, const Fr& x) {
+  uint32_t p = pad_idx(l);
+#pragma unroll
+  for (int k = 0; k < 8; k++) sm[k * plane + p] = x.v[k];
+}
+__device__ __forceinline__ Fr g_load(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void g_store(Fr* p, const Fr& x) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+
+// One radix-2 stage on the shared tile.  sl = stage index inside the pass (global bit s = lo + sl).
+// low_bits = the fixed low index bits of this tile below `lo` other than the `cb` column bits.
+template <bool DIT>
+__device__ __forceinline__ void tile_stage(uint32_t* sm, uint32_t plane, uint32_t tile_elems, const Fr* tw, int log_n,
+                                           int lo, int sl, int cb, uint32_t low_bits) {
+  const int lb = sl + cb;        // local bit that this stage pairs
+  const int s = lo + sl;         // global bit
+  const uint32_t cmask = (1u << cb) - 1;
+  for (uint32_t b = threadIdx.x; b < (tile_elems >> 1); b += blockDim.x) {
+    uint32_t l0 = ((b >> lb) << (lb + 1)) | (b & ((1u << lb) - 1));
+    uint32_t l1 = l0 | (1u << lb);
+    uint32_t t = l0 >> cb;
+    uint32_t imod = ((t & ((1u << sl) - 1)) << lo) | low_bits | (l0 & cmask);  // global index mod 2^s
+    uint32_t e = imod << (log_n - 1 - s);                                      // exponent of w, < n/2
+    Fr u = sm_load(sm, plane, l0);
+    Fr v = sm_load(sm, plane, l1);
+    if (DIT) {
+      if (e) v = fp_mul(v, g_load(tw + e));
+      sm_store(sm, plane, l0, fp_add(u, v));
+      sm_store(sm, plane, l1, fp_sub(u, v));
+    } else {
+      Fr d = fp_sub(u, v);
+      if (e) d = fp_mul(d, g_load(tw + e));
+      sm_store(sm, plane, l0, fp_add(u, v));
+      sm_store(sm, plane, l1, d);
+    }
+  }
+}
+
+// Generic pass over global bits [lo, lo+ns).  Tile = 2^ns "rows" x 2^cb adjacent columns (cb <= lo).
+// grid.x = n >> (ns + cb) tiles, grid.y = batch.
+template <bool DIT>
+__global__ void __launch_bounds__(kNttThreads)
+ntt_pass_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw, int log_n, int lo, int ns, int cb) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t tile_elems = 1u << (ns + cb);
+  const uint32_t plane = tile_elems + (tile_elems >> 5) + 1;
+  Fr* x = data + ((size_t)blockIdx.y << log_n);
+  const uint32_t lhi_bits = lo - cb;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t lhi = tile & ((1u << lhi_bits) - 1);
+  const uint32_t upper = tile >> lhi_bits;
+  const uint32_t low_bits = lhi << cb;
+  const uint32_t base = (upper << (lo + ns)) | low_bits;
+  const uint32_t cmask = (1u << cb) - 1;
+  for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) {
+    uint32_t gi = base | ((l >> cb) << lo) | (l & cmask);
+    sm_store(sm, plane, l, g_load(x + gi));
+  }
+  __syncthreads();
+  if (DIT) {
+    for (int sl = 0; sl < ns; sl++) {
+      tile_stage<true>(sm, plane, tile_elems, tw, log_n, lo, sl, cb, low_bits);
+      __syncthreads();
+    }
+  } else {
+    for (int sl = ns - 1; sl >= 0; sl--) {
+      tile_stage<false>(sm, plane, tile_elems, tw, log_n, lo, sl, cb, low_bits);
+      __syncthreads();
+    }
+  }
+  for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) {
+    uint32_t gi = base | ((l >> cb) << lo) | (l & cmask);
+    g_store(x + gi, sm_load(sm, plane, l));
+  }
+}
+
+// Low pass of the pipeline: DIF stages ns-1..0 (inverse twiddles), scale by n^-1 * inc^bitrev(p), DIT stages
+// 0..ns-1 (forward twiddles).  Contiguous tile of 2^ns elements.
+__global__ void __launch_bounds__(kNttThreads)
+ntt_fused_lo_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw_inv, const Fr* __restrict__ tw_fwd,
+                    const Fr* __restrict__ scale, int log_n, int ns) {
+  extern __shared__ uint32_t sm[];
+  const uint32_t tile_elems = 1u << ns;
+  const uint32_t plane = tile_elems + (tile_elems >> 5) + 1;
+  Fr* x = data + ((size_t)blockIdx.y << log_n);
+  const uint32_t base = blockIdx.x << ns;
+  for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) sm_store(sm, plane, l, g_load(x + base + l));
+  __syncthreads();
+  for (int sl = ns - 1; sl >= 0; sl--) {
+    tile_stage<false>(sm, plane, tile_elems, tw_inv, log_n, 0, sl, 0, 0);
+    __syncthreads();
+  }
+  for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) {
+    Fr v = sm_load(sm, plane, l);
+    sm_store(sm, plane, l, fp_mul(v, g_load(scale + base + l)));
+  }
+  __syncthreads();
+  for (int sl = 0; sl < ns; sl++) {
+    tile_stage<true>(sm, plane, tile_elems, tw_fwd, log_n, 0, sl, 0, 0);
+    __syncthreads();
+  }
+  for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) g_store(x + base + l, sm_load(sm, plane, l));
+}
+
+__global__ void bitrev_permute_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, int log_n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((size_t)1 << log_n)) return;
+  uint32_t j = log_n ? (__brev((uint32_t)i) >> (32 - log_n)) : 0;
+  g_store(out + j, g_load(in + i));
+}
+
+__global__ void scale_const_kernel(Fr* __restrict__ data, const Fr* __restrict__ k, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  g_store(data + i, fp_mul(g_load(data + i), g_load(k)));
+}
+
+__global__ void join_abc_kernel(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c,
+                                Fr* __restrict__ h, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr t = fp_sub(fp_mul(g_load(a + i), g_load(b + i)), g_load(c + i));
+  g_store(h + i, fp_from_mont(t));
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static Fr host_fr_from_u64(uint64_t x) {
+  Fr t = Fr::zero();
+  t.v[0] = (uint32_t)x;
+  t.v[1] = (uint32_t)(x >> 32);
+  return fp_to_mont(t);
+}
+
+// w[k]: primitive 2^k-th root of unity, ffjavascript convention (nqr = 5, w[28] = 5^((r-1)/2^28), w[k-1] = w[k]^2).
+Fr host_fr_root(int k) {
+  uint32_t e[8];
+  for (int i = 0; i < 8; i++) e[i] = FrParams::mod(i);
+  e[0] -= 1;
+  // e >>= 28
+  uint32_t t[8];
+  for (int i = 0; i < 8; i++) {
+    uint64_t lo = e[i] >> 28;
+    uint64_t hi = (i + 1 < 8) ? ((uint64_t)e[i + 1] << 4) : 0;
+    t[i] = (uint32_t)(lo | hi);
+  }
+  Fr w = fp_pow(host_fr_from_u64(5), t);
+  for (int i = 28; i > k; i--) w = fp_sqr(w);
+  return w;
+}
+
+static size_t pass_smem_bytes(int ns, int cb) {
+  size_t tile = (size_t)1 << (ns + cb);
+  return 8 * (tile + (tile >> 5) + 1) * sizeof(uint32_t);
+}
+
+static void ensure_smem_attrs() {
+  static bool done = false;
+  if (done) return;
+  int mx = (int)pass_smem_bytes(kMaxPassBits, 1);
+  NZCP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  NZCP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  NZCP_CUDA(cudaFuncSetAttribute(ntt_fused_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  done = true;
+}
+
+void ntt_domain_create(NttDomain* d, int log_n, cudaStream_t st) {
+  if (log_n < 1 || log_n > 27) throw std::runtime_error("ntt: unsupported domain size");
+  d->log_n = log_n;
+  size_t n = (size_t)1 << log_n;
+  std::vector<Fr> fwd(n / 2), inv(n / 2), scale(n);
+  Fr w = host_fr_root(log_n);
+  Fr winv = fp_inv(w);
+  Fr a = Fr::one(), b = Fr::one();
+  for (size_t j = 0; j < n / 2; j++) {
+    fwd[j] = a;
+    inv[j] = b;
+    a = fp_mul(a, w);
+    b = fp_mul(b, winv);
+  }
+  Fr ninv = fp_inv(host_fr_from_u64(n));
+  Fr inc = (log_n == 28) ? host_fr_from_u64(25) : host_fr_root(log_n + 1);  // snarkjs: Fr.shift when power == Fr.s
+  Fr k = ninv;
+  for (size_t j = 0; j < n; j++) {
+    uint32_t p = 0;
+    for (int bit = 0; bit < log_n; bit++) p |= ((j >> bit) & 1) << (log_n - 1 - bit);
+    scale[p] = k;
+    k = fp_mul(k, inc);
+  }
+  NZCP_CUDA(cudaMalloc(&d->tw_fwd, (n / 2) * sizeof(Fr)));
+  NZCP_CUDA(cudaMalloc(&d->tw_inv, (n / 2) * sizeof(Fr)));
+  NZCP_CUDA(cudaMalloc(&d->coset_scale, n * sizeof(Fr)));
+  NZCP_CUDA(cudaMalloc(&d->ninv_scale, sizeof(Fr)));
+  NZCP_CUDA(cudaMemcpyAsync(d->tw_fwd, fwd.data(), (n / 2) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  NZCP_CUDA(cudaMemcpyAsync(d->tw_inv, inv.data(), (n / 2) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  NZCP_CUDA(cudaMemcpyAsync(d->coset_scale, scale.data(), n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  NZCP_CUDA(cudaMemcpyAsync(d->ninv_scale, &ninv, sizeof(Fr), cudaMemcpyHostToDevice, st));
+  NZCP_CUDA(cudaStreamSynchronize(st));
+}
+
+void ntt_domain_destroy(NttDomain* d) {
+  cudaFree(d->tw_fwd);
+  cudaFree(d->tw_inv);
+  cudaFree(d->coset_scale);
+  cudaFree(d->ninv_scale);
+  *d = NttDomain();
+}
+
+// Split bits [lo_bits, log_n) into hi passes of <= kMaxPassBits stages each.
+static std::vector<std::pair<int, int>> hi_passes(int log_n, int lo_bits) {
+  std::vector<std::pair<int, int>> v;  // (lo, ns)
+  int rem = log_n - lo_bits;
+  if (rem <= 0) return v;
+  int np = (rem + kMaxPassBits - 1) / kMaxPassBits;
+  int lo = lo_bits;
+  for (int i = 0; i < np; i++) {
+    int ns = rem / np + (i < rem % np ? 1 : 0);
+    v.push_back({lo, ns});
+    lo += ns;
+  }
+  return v;
+}
+
+template <bool DIT>
+static void launch_pass(Fr* data, const Fr* tw, int log_n, int lo, int ns, int batch, cudaStream_t st) {
+  int cb = lo >= 1 ? 1 : 0;
+  dim3 grid(1u << (log_n - ns - cb), batch);
+  ntt_pass_kernel<DIT><<<grid, kNttThreads, pass_smem_bytes(ns, cb), st>>>(data, tw, log_n, lo, ns, cb);
+  NZCP_LAUNCH_CHECK();
+}
+
+void ntt_coset_pipeline(const NttDomain& d, Fr* data, int batch, cudaStream_t st) {
+  ensure_smem_attrs();
+  int lo_bits = d.log_n < kMaxPassBits ? d.log_n : kMaxPassBits;
+  auto hp = hi_passes(d.log_n, lo_bits);
+  for (int i = (int)hp.size() - 1; i >= 0; i--)
+    launch_pass<false>(data, d.tw_inv, d.log_n, hp[i].first, hp[i].second, batch, st);
+  dim3 grid(1u << (d.log_n - lo_bits), batch);
+  ntt_fused_lo_kernel<<<grid, kNttThreads, pass_smem_bytes(lo_bits, 0), st>>>(data, d.tw_inv, d.tw_fwd, d.coset_scale,
+                                                                              d.log_n, lo_bits);
+  NZCP_LAUNCH_CHECK();
+  for (size_t i = 0; i < hp.size(); i++) launch_pass<true>(data, d.tw_fwd, d.log_n, hp[i].first, hp[i].second, batch, st);
+}
+
+static void ntt_natural(const NttDomain& d, Fr* data, Fr* tmp, const Fr* tw, cudaStream_t st) {
+  ensure_smem_attrs();
+  size_t n = (size_t)1 << d.log_n;
+  bitrev_permute_kernel<<<div_up(n, 256), 256, 0, st>>>(data, tmp, d.log_n);
+  NZCP_LAUNCH_CHECK();
+  int lo_bits = d.log_n < kMaxPassBits ? d.log_n : kMaxPassBits;
+  launch_pass<true>(tmp, tw, d.log_n, 0, lo_bits, 1, st);
+  auto hp = hi_passes(d.log_n, lo_bits);
+  for (size_t i = 0; i < hp.size(); i++) launch_pass<true>(tmp, tw, d.log_n, hp[i].first, hp[i].second, 1, st);
+  NZCP_CUDA(cudaMemcpyAsync(data, tmp, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+}
+
+void ntt_forward(const NttDomain& d, Fr* data, Fr* tmp, cudaStream_t st) { ntt_natural(d, data, tmp, d.tw_fwd, st); }
+
+void ntt_inverse(const NttDomain& d, Fr* data, Fr* tmp, cudaStream_t st) {
+  ntt_natural(d, data, tmp, d.tw_inv, st);
+  size_t n = (size_t)1 << d.log_n;
+  scale_const_kernel<<<div_up(n, 256), 256, 0, st>>>(data, d.ninv_scale, n);
+  NZCP_LAUNCH_CHECK();
+}
+
+void ntt_join_abc(const Fr* a, const Fr* b, const Fr* c, Fr* h, size_t n, cudaStream_t st) {
+  join_abc_kernel<<<div_up(n, 256), 256, 0, st>>>(a, b, c, h, n);
+  NZCP_LAUNCH_CHECK();
+}
+
+}  // namespace nzcp

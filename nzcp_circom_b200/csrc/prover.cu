@@ -1,0 +1,440 @@
+// groth16.prove on one B200: zkey resident in HBM, one call per proof.
+//
+// Replaces snarkjs 0.4.12 src/groth16_prove.js groth16Prove() (upstream, not vendored: package.json:12,
+// yarn.lock:987-999) together with the container readers it uses (@iden3/binfileutils readBinFile/readSection,
+// snarkjs src/zkey_utils.js readHeader, src/wtns_utils.js readHeader).  Order of work and every formula follow
+// that function: buildABC1 -> (ifft, batchApplyKey, fft) x3 -> joinABC -> 5 multiexps -> r/s blinding -> affine.
+// Differences that do not change any output bit: sections 4-9 are parsed and uploaded once per zkey instead of
+// re-read per proof; the COO coefficient list is regrouped to CSR; the four witness MSMs run on their own streams
+// concurrently with the H pipeline.
+#include <memory>
+#include <mutex>
+
+#include "api_util.cuh"
+
+namespace nzcp {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& s) { t_last_error = s; }
+
+// ---------------------------------------------------------------------------------------------- container parsing
+struct Section {
+  const uint8_t* p = nullptr;
+  uint64_t len = 0;
+};
+
+static uint32_t rd32(const uint8_t* p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+static uint64_t rd64(const uint8_t* p) {
+  uint64_t v;
+  memcpy(&v, p, 8);
+  return v;
+}
+
+// binfileutils readBinFile: magic, version, nSections, then (u32 id, u64 len, payload)*
+static void parse_container(const uint8_t* b, size_t len, const char magic[4], uint32_t max_version, Section* secs,
+                            int max_id) {
+  if (len < 12 || memcmp(b, magic, 4) != 0) throw ApiError(NZCP_E_FORMAT, std::string(magic, 4) + " file: Invalid File format");
+  uint32_t version = rd32(b + 4);
+  if (version > max_version) throw ApiError(NZCP_E_FORMAT, "Version not supported");
+  uint32_t nsec = rd32(b + 8);
+  size_t pos = 12;
+  for (uint32_t i = 0; i < nsec; i++) {
+    if (pos + 12 > len) throw ApiError(NZCP_E_FORMAT, "truncated section table");
+    uint32_t id = rd32(b + pos);
+    uint64_t sl = rd64(b + pos + 4);
+    pos += 12;
+    if (sl > len - pos) throw ApiError(NZCP_E_FORMAT, "section exceeds file size");
+    if ((int)id <= max_id && secs[id].p == nullptr) {
+      secs[id].p = b + pos;
+      secs[id].len = sl;
+    }
+    pos += sl;
+  }
+}
+
+}  // namespace nzcp
+
+using namespace nzcp;
+
+struct nzcp_zkey {
+  int device = 0;
+  uint32_t n_vars = 0, n_public = 0, domain_size = 0, power = 0;
+  uint64_t n_coefs = 0;
+  G1Affine alpha1, beta1, delta1;  // Montgomery affine, as stored
+  G2Affine beta2, gamma2, delta2;
+  R1csDevice r1cs;
+  G1Affine *d_A = nullptr, *d_B1 = nullptr, *d_C = nullptr, *d_H = nullptr;
+  G2Affine* d_B2 = nullptr;
+  NttDomain dom;
+  size_t device_bytes = 0;
+};
+
+struct nzcp_prover {
+  nzcp_zkey* zk = nullptr;
+  cudaStream_t st_main = nullptr;
+  cudaStream_t st_msm[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[16];
+  int n_ev = 0;
+  Fr* d_wtns = nullptr;
+  Fr* d_abc = nullptr;
+  Fr* d_h = nullptr;
+  MsmPlan plan_a, plan_b1, plan_b2, plan_c, plan_h;
+};
+
+namespace nzcp {
+
+static void zkey_release(nzcp_zkey* zk) {
+  if (!zk) return;
+  cudaSetDevice(zk->device);
+  cudaFree(zk->r1cs.row_ptr);
+  cudaFree(zk->r1cs.col);
+  cudaFree(zk->r1cs.val);
+  cudaFree(zk->d_A);
+  cudaFree(zk->d_B1);
+  cudaFree(zk->d_B2);
+  cudaFree(zk->d_C);
+  cudaFree(zk->d_H);
+  ntt_domain_destroy(&zk->dom);
+  delete zk;
+}
+
+template <class T>
+static T* upload(const void* src, size_t bytes, size_t* total) {
+  T* d = nullptr;
+  NZCP_CUDA(cudaMalloc(&d, bytes ? bytes : 16));
+  if (bytes) NZCP_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+  *total += bytes;
+  return d;
+}
+
+static nzcp_zkey* zkey_load_impl(const uint8_t* b, size_t len, int device) {
+  Section s[11];
+  parse_container(b, len, "zkey", 1, s, 10);
+  if (!s[1].p || s[1].len < 4) throw ApiError(NZCP_E_FORMAT, "zkey: missing section 1");
+  if (rd32(s[1].p) != 1) throw ApiError(NZCP_E_NOT_GROTH16, "zkey file is not groth16");
+  for (int id = 2; id <= 9; id++)
+    if (!s[id].p) throw ApiError(NZCP_E_FORMAT, "zkey: missing section " + std::to_string(id));
+  // section 2: header (zkey_utils.js readHeaderGroth16)
+  const uint8_t* h = s[2].p;
+  const size_t hdr_len = 4 + 32 + 4 + 32 + 12 + 64 + 64 + 128 + 128 + 64 + 128;
+  if (s[2].len < hdr_len) throw ApiError(NZCP_E_FORMAT, "zkey: short header");
+  if (rd32(h) != 32 || rd32(h + 36) != 32) throw ApiError(NZCP_E_CURVE, "zkey: field size is not 32 bytes (curve is not bn128)");
+  if (memcmp(h + 4, kQBytes, 32) != 0 || memcmp(h + 40, kRBytes, 32) != 0)
+    throw ApiError(NZCP_E_CURVE, "zkey: curve is not bn128");
+  std::unique_ptr<nzcp_zkey, void (*)(nzcp_zkey*)> zk(new nzcp_zkey(), zkey_release);
+  zk->device = device;
+  zk->n_vars = rd32(h + 72);
+  zk->n_public = rd32(h + 76);
+  zk->domain_size = rd32(h + 80);
+  uint32_t n = zk->domain_size;
+  if (n < 2 || (n & (n - 1)) != 0) throw ApiError(NZCP_E_FORMAT, "zkey: domainSize is not a power of two >= 2");
+  if (zk->n_public + 1 > zk->n_vars) throw ApiError(NZCP_E_FORMAT, "zkey: nPublic + 1 > nVars");
+  while ((1u << zk->power) < n) zk->power++;
+  const uint8_t* pp = h + 84;
+  memcpy(&zk->alpha1, pp, 64); pp += 64;
+  memcpy(&zk->beta1, pp, 64); pp += 64;
+  memcpy(&zk->beta2, pp, 128); pp += 128;
+  memcpy(&zk->gamma2, pp, 128); pp += 128;
+  memcpy(&zk->delta1, pp, 64); pp += 64;
+  memcpy(&zk->delta2, pp, 128);
+  // section sizes
+  const uint64_t m = zk->n_vars;
+  if (s[5].len != m * 64 || s[6].len != m * 64 || s[7].len != m * 128 || s[8].len != (m - zk->n_public - 1) * 64 ||
+      s[9].len != (uint64_t)n * 64)
+    throw ApiError(NZCP_E_FORMAT, "zkey: point section size does not match header");
+  // section 4: COO coefficients -> CSR (rows 0..n-1 = A, n..2n-1 = B)
+  if (s[4].len < 4) throw ApiError(NZCP_E_FORMAT, "zkey: short coefficient section");
+  uint64_t nc = rd32(s[4].p);
+  if (s[4].len != 4 + nc * 44) throw ApiError(NZCP_E_FORMAT, "zkey: coefficient section size mismatch");
+  zk->n_coefs = nc;
+  std::vector<uint32_t> row_ptr(2 * (size_t)n + 1, 0);
+  const uint8_t* cp = s[4].p + 4;
+  for (uint64_t i = 0; i < nc; i++) {
+    const uint8_t* rec = cp + i * 44;
+    uint32_t mtx = rd32(rec), c = rd32(rec + 4), sg = rd32(rec + 8);
+    if (mtx > 1 || c >= n || sg >= zk->n_vars) throw ApiError(NZCP_E_FORMAT, "zkey: coefficient record out of range");
+    row_ptr[(size_t)mtx * n + c + 1]++;
+  }
+  for (size_t i = 0; i < 2 * (size_t)n; i++) row_ptr[i + 1] += row_ptr[i];
+  std::vector<uint32_t> fill(row_ptr.begin(), row_ptr.end() - 1);
+  std::vector<uint32_t> col(nc ? nc : 1);
+  std::vector<Fr> val(nc ? nc : 1);
+  for (uint64_t i = 0; i < nc; i++) {
+    const uint8_t* rec = cp + i * 44;
+    uint32_t mtx = rd32(rec), c = rd32(rec + 4), sg = rd32(rec + 8);
+    uint32_t pos = fill[(size_t)mtx * n + c]++;
+    col[pos] = sg;
+    memcpy(val[pos].v, rec + 12, 32);
+  }
+  use_device(device);
+  size_t tot = 0;
+  zk->r1cs.n = n;
+  zk->r1cs.nnz = nc;
+  zk->r1cs.row_ptr = upload<uint32_t>(row_ptr.data(), row_ptr.size() * 4, &tot);
+  zk->r1cs.col = upload<uint32_t>(col.data(), nc * 4, &tot);
+  zk->r1cs.val = upload<Fr>(val.data(), nc * 32, &tot);
+  zk->d_A = upload<G1Affine>(s[5].p, s[5].len, &tot);
+  zk->d_B1 = upload<G1Affine>(s[6].p, s[6].len, &tot);
+  zk->d_B2 = upload<G2Affine>(s[7].p, s[7].len, &tot);
+  zk->d_C = upload<G1Affine>(s[8].p, s[8].len, &tot);
+  zk->d_H = upload<G1Affine>(s[9].p, s[9].len, &tot);
+  ntt_domain_create(&zk->dom, (int)zk->power, 0);
+  tot += ((size_t)n / 2 * 2 + n) * sizeof(Fr);
+  zk->device_bytes = tot;
+  return zk.release();
+}
+
+static void prover_release(nzcp_prover* p) {
+  if (!p) return;
+  cudaSetDevice(p->zk->device);
+  if (p->st_main) cudaStreamDestroy(p->st_main);
+  for (int i = 0; i < 4; i++)
+    if (p->st_msm[i]) cudaStreamDestroy(p->st_msm[i]);
+  for (int i = 0; i < p->n_ev; i++) cudaEventDestroy(p->ev[i]);
+  cudaFree(p->d_wtns);
+  cudaFree(p->d_abc);
+  cudaFree(p->d_h);
+  msm_plan_destroy(&p->plan_a);
+  msm_plan_destroy(&p->plan_b1);
+  msm_plan_destroy(&p->plan_b2);
+  msm_plan_destroy(&p->plan_c);
+  msm_plan_destroy(&p->plan_h);
+  delete p;
+}
+
+static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
+  use_device(zk->device);
+  std::unique_ptr<nzcp_prover, void (*)(nzcp_prover*)> p(new nzcp_prover(), prover_release);
+  p->zk = zk;
+  NZCP_CUDA(cudaStreamCreateWithFlags(&p->st_main, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) NZCP_CUDA(cudaStreamCreateWithFlags(&p->st_msm[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) {
+    NZCP_CUDA(cudaEventCreate(&p->ev[i]));
+    p->n_ev = i + 1;
+  }
+  size_t n = zk->domain_size;
+  NZCP_CUDA(cudaMalloc(&p->d_wtns, (size_t)zk->n_vars * sizeof(Fr)));
+  NZCP_CUDA(cudaMalloc(&p->d_abc, 3 * n * sizeof(Fr)));
+  NZCP_CUDA(cudaMalloc(&p->d_h, n * sizeof(Fr)));
+  msm_plan_create(&p->plan_a, zk->n_vars, false, 0);
+  msm_plan_create(&p->plan_b1, zk->n_vars, false, 0);
+  msm_plan_create(&p->plan_b2, zk->n_vars, true, 0);
+  msm_plan_create(&p->plan_c, zk->n_vars - zk->n_public - 1, false, 0);
+  msm_plan_create(&p->plan_h, n, false, 0);
+  return p.release();
+}
+
+static void random_fr(uint8_t out[32]) {
+  FILE* f = fopen("/dev/urandom", "rb");
+  if (!f) throw ApiError(NZCP_E_INTERNAL, "cannot open /dev/urandom");
+  for (;;) {
+    if (fread(out, 1, 32, f) != 32) {
+      fclose(f);
+      throw ApiError(NZCP_E_INTERNAL, "short read from /dev/urandom");
+    }
+    out[31] &= 0x3f;  // < 2^254; rejection-sample into [0, r)
+    if (fr_bytes_canonical(out)) break;
+  }
+  fclose(f);
+}
+
+// Event slots: 0 start, 1 upload done, 2 eval done, 3 ntt+join done, 4 msm H done, 5..12 msm A,B1,B2,C (begin,end)
+static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_witness_ext, const uint8_t* r_in,
+                       const uint8_t* s_in, nzcp_proof* proof, nzcp_prove_debug* dbg) {
+  nzcp_zkey* zk = p->zk;
+  if (!proof) throw ApiError(NZCP_E_ARG, "proof pointer is null");
+  uint8_t rb[32], sb[32];
+  if (r_in) memcpy(rb, r_in, 32); else random_fr(rb);
+  if (s_in) memcpy(sb, s_in, 32); else random_fr(sb);
+  if (!fr_bytes_canonical(rb) || !fr_bytes_canonical(sb)) throw ApiError(NZCP_E_ARG, "blinding scalar r or s is not < r");
+  use_device(zk->device);
+  const size_t n = zk->domain_size, m = zk->n_vars, npub = zk->n_public;
+  cudaStream_t sm = p->st_main;
+  NZCP_CUDA(cudaEventRecord(p->ev[0], sm));
+  const Fr* d_w = d_witness_ext;
+  if (h_witness) {
+    NZCP_CUDA(cudaMemcpyAsync(p->d_wtns, h_witness, m * sizeof(Fr), cudaMemcpyHostToDevice, sm));
+    d_w = p->d_wtns;
+  }
+  NZCP_CUDA(cudaEventRecord(p->ev[1], sm));
+  // witness MSMs on their own streams (snarkjs order: A, B1, B2, C)
+  struct Job { MsmPlan* plan; const void* bases; const Fr* sc; size_t cnt; };
+  Job jobs[4] = {{&p->plan_a, zk->d_A, d_w, m},
+                 {&p->plan_b1, zk->d_B1, d_w, m},
+                 {&p->plan_b2, zk->d_B2, d_w, m},
+                 {&p->plan_c, zk->d_C, d_w + npub + 1, m - npub - 1}};
+  for (int k = 0; k < 4; k++) {
+    NZCP_CUDA(cudaStreamWaitEvent(p->st_msm[k], p->ev[1], 0));
+    NZCP_CUDA(cudaEventRecord(p->ev[5 + 2 * k], p->st_msm[k]));
+    msm_launch(jobs[k].plan, jobs[k].bases, jobs[k].sc, jobs[k].cnt, p->st_msm[k]);
+    NZCP_CUDA(cudaEventRecord(p->ev[6 + 2 * k], p->st_msm[k]));
+  }
+  // H pipeline on the main stream
+  r1cs_eval(zk->r1cs, d_w, p->d_abc, sm);
+  NZCP_CUDA(cudaEventRecord(p->ev[2], sm));
+  ntt_coset_pipeline(zk->dom, p->d_abc, 3, sm);
+  ntt_join_abc(p->d_abc, p->d_abc + n, p->d_abc + 2 * n, p->d_h, n, sm);
+  NZCP_CUDA(cudaEventRecord(p->ev[3], sm));
+  msm_launch(&p->plan_h, zk->d_H, p->d_h, n, sm);
+  NZCP_CUDA(cudaEventRecord(p->ev[4], sm));
+  if (dbg && dbg->h_scalars) NZCP_CUDA(cudaMemcpyAsync(dbg->h_scalars, p->d_h, n * sizeof(Fr), cudaMemcpyDeviceToHost, sm));
+  for (int k = 0; k < 4; k++) NZCP_CUDA(cudaStreamSynchronize(p->st_msm[k]));
+  NZCP_CUDA(cudaStreamSynchronize(sm));
+
+  G1XYZZ A, B1, C, H;
+  G2XYZZ B2;
+  try {
+    A = msm_finish_g1(&p->plan_a);
+    B1 = msm_finish_g1(&p->plan_b1);
+    B2 = msm_finish_g2(&p->plan_b2);
+    C = msm_finish_g1(&p->plan_c);
+    H = msm_finish_g1(&p->plan_h);
+  } catch (const std::runtime_error& e) {
+    throw ApiError(NZCP_E_RANGE, e.what());
+  }
+  if (dbg) {
+    g1_to_plain_bytes(A, dbg->msm_a);
+    g1_to_plain_bytes(B1, dbg->msm_b1);
+    g2_to_plain_bytes(B2, dbg->msm_b2);
+    g1_to_plain_bytes(C, dbg->msm_c);
+    g1_to_plain_bytes(H, dbg->msm_h);
+    float t;
+    auto el = [&](int a, int b) { cudaEventElapsedTime(&t, p->ev[a], p->ev[b]); return t; };
+    dbg->stage_ms[0] = el(0, 1);
+    dbg->stage_ms[1] = el(1, 2);
+    dbg->stage_ms[2] = el(2, 3);
+    dbg->stage_ms[3] = el(5, 6);
+    dbg->stage_ms[4] = el(7, 8);
+    dbg->stage_ms[5] = el(9, 10);
+    dbg->stage_ms[6] = el(11, 12);
+    dbg->stage_ms[7] = el(3, 4);
+  }
+  // finalisation (tail of groth16Prove): O(1) group operations on the host, as snarkjs does on its main thread
+  Fr r = fp_from_bytes_plain<FrParams>(rb), s = fp_from_bytes_plain<FrParams>(sb);
+  Fr rs = fp_from_mont(fp_mul(fp_to_mont(r), fp_to_mont(s)));
+  Fr neg_rs = fp_neg(rs);
+  G1XYZZ d1 = G1XYZZ::from_affine(zk->delta1);
+  G2XYZZ d2 = G2XYZZ::from_affine(zk->delta2);
+  G1XYZZ pi_a = A;
+  xyzz_add(pi_a, G1XYZZ::from_affine(zk->alpha1));
+  xyzz_add(pi_a, xyzz_mul(d1, r.v));
+  G2XYZZ pi_b = B2;
+  xyzz_add(pi_b, G2XYZZ::from_affine(zk->beta2));
+  xyzz_add(pi_b, xyzz_mul(d2, s.v));
+  G1XYZZ pib1 = B1;
+  xyzz_add(pib1, G1XYZZ::from_affine(zk->beta1));
+  xyzz_add(pib1, xyzz_mul(d1, s.v));
+  G1XYZZ pi_c = C;
+  xyzz_add(pi_c, H);
+  xyzz_add(pi_c, xyzz_mul(pi_a, s.v));
+  xyzz_add(pi_c, xyzz_mul(pib1, r.v));
+  xyzz_add(pi_c, xyzz_mul(d1, neg_rs.v));
+  g1_to_plain_bytes(pi_a, proof->pi_a);
+  g2_to_plain_bytes(pi_b, proof->pi_b);
+  g1_to_plain_bytes(pi_c, proof->pi_c);
+}
+
+}  // namespace nzcp
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* nzcp_last_error(void) { return t_last_error.c_str(); }
+
+int nzcp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int nzcp_zkey_load(const uint8_t* bytes, size_t len, int device, nzcp_zkey** out) {
+  return api_guard([&] {
+    if (!bytes || !out) throw ApiError(NZCP_E_ARG, "null argument");
+    *out = nullptr;
+    *out = zkey_load_impl(bytes, len, device);
+  });
+}
+
+int nzcp_zkey_info_get(const nzcp_zkey* zk, nzcp_zkey_info* info) {
+  return api_guard([&] {
+    if (!zk || !info) throw ApiError(NZCP_E_ARG, "null argument");
+    memset(info, 0, sizeof *info);
+    info->n_vars = zk->n_vars;
+    info->n_public = zk->n_public;
+    info->domain_size = zk->domain_size;
+    info->power = zk->power;
+    info->n_coefs = zk->n_coefs;
+    info->device_bytes = zk->device_bytes;
+    g1_to_plain_bytes(G1XYZZ::from_affine(zk->alpha1), info->alpha1);
+    g1_to_plain_bytes(G1XYZZ::from_affine(zk->beta1), info->beta1);
+    g1_to_plain_bytes(G1XYZZ::from_affine(zk->delta1), info->delta1);
+    g2_to_plain_bytes(G2XYZZ::from_affine(zk->beta2), info->beta2);
+    g2_to_plain_bytes(G2XYZZ::from_affine(zk->gamma2), info->gamma2);
+    g2_to_plain_bytes(G2XYZZ::from_affine(zk->delta2), info->delta2);
+  });
+}
+
+void nzcp_zkey_free(nzcp_zkey* zk) { zkey_release(zk); }
+
+int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out) {
+  return api_guard([&] {
+    if (!zk || !out) throw ApiError(NZCP_E_ARG, "null argument");
+    *out = nullptr;
+    *out = prover_create_impl(zk);
+  });
+}
+
+void nzcp_prover_free(nzcp_prover* p) { prover_release(p); }
+
+int nzcp_prove(nzcp_prover* p, const uint8_t* wtns, size_t wtns_len, const uint8_t* r, const uint8_t* s,
+               nzcp_proof* proof, nzcp_prove_debug* dbg) {
+  return api_guard([&] {
+    if (!p || !wtns) throw ApiError(NZCP_E_ARG, "null argument");
+    Section sec[3];
+    parse_container(wtns, wtns_len, "wtns", 2, sec, 2);
+    if (!sec[1].p || !sec[2].p || sec[1].len < 8) throw ApiError(NZCP_E_FORMAT, "wtns: missing section");
+    uint32_t n8 = rd32(sec[1].p);
+    if (n8 != 32 || sec[1].len != 4 + 32 + 4 || memcmp(sec[1].p + 4, kRBytes, 32) != 0)
+      throw ApiError(NZCP_E_CURVE, "Curve of the witness does not match the curve of the proving key");
+    uint32_t nw = rd32(sec[1].p + 36);
+    if (nw != p->zk->n_vars)
+      throw ApiError(NZCP_E_WITNESS_LEN, "Invalid witness length. Circuit: " + std::to_string(p->zk->n_vars) +
+                                             ", witness: " + std::to_string(nw));
+    if (sec[2].len != (uint64_t)nw * 32) throw ApiError(NZCP_E_FORMAT, "wtns: section 2 size mismatch");
+    prove_impl(p, sec[2].p, nullptr, r, s, proof, dbg);
+  });
+}
+
+int nzcp_prove_witness(nzcp_prover* p, const uint8_t* witness, uint32_t n_witness, const uint8_t* r, const uint8_t* s,
+                       nzcp_proof* proof, nzcp_prove_debug* dbg) {
+  return api_guard([&] {
+    if (!p || !witness) throw ApiError(NZCP_E_ARG, "null argument");
+    if (n_witness != p->zk->n_vars)
+      throw ApiError(NZCP_E_WITNESS_LEN, "Invalid witness length. Circuit: " + std::to_string(p->zk->n_vars) +
+                                             ", witness: " + std::to_string(n_witness));
+    prove_impl(p, witness, nullptr, r, s, proof, dbg);
+  });
+}
+
+int nzcp_prove_device(nzcp_prover* p, const void* d_witness, const uint8_t* r, const uint8_t* s, nzcp_proof* proof,
+                      nzcp_prove_debug* dbg) {
+  return api_guard([&] {
+    if (!p || !d_witness) throw ApiError(NZCP_E_ARG, "null argument");
+    prove_impl(p, nullptr, reinterpret_cast<const Fr*>(d_witness), r, s, proof, dbg);
+  });
+}
+
+void* nzcp_prover_witness_buffer(nzcp_prover* p) { return p ? p->d_wtns : nullptr; }
+
+uint64_t nzcp_prover_launch_count(const nzcp_prover*) { return g_launch_count.load(); }
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// Stand-alone entry points: NTT / MSM sweeps (BASELINE.json config 4) and the device self-tests the parity suite uses.
+// Each call allocates, runs, times with CUDA events on the launching stream, and frees -- they are measurement and
+// test hooks, not the proving path (that is prover.cu, which keeps everything resident).
+#include <memory>
+
+#include "api_util.cuh"
+
+namespace nzcp {
+
+G1Affine g1_generator();  // synth.cu
+Fr host_fr_root(int k);     // ntt.cu
+G2Affine g2_generator();
+
+struct DevBuf {
+  void* p = nullptr;
+  explicit DevBuf(size_t bytes) { NZCP_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); }
+  ~DevBuf() { cudaFree(p); }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Timer {
+  cudaEvent_t a, b;
+  cudaStream_t st;
+  explicit Timer(cudaStream_t s) : st(s) {
+    NZCP_CUDA(cudaEventCreate(&a));
+    NZCP_CUDA(cudaEventCreate(&b));
+    NZCP_CUDA(cudaEventRecord(a, st));
+  }
+  float stop() {
+    float ms = 0;
+    NZCP_CUDA(cudaEventRecord(b, st));
+    NZCP_CUDA(cudaEventSynchronize(b));
+    NZCP_CUDA(cudaEventElapsedTime(&ms, a, b));
+    return ms;
+  }
+  ~Timer() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ self-test kernels
+template <class P>
+__global__ void field_op_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp<P> x = a[i], y = b[i], r;
+  switch (op) {
+    case 0: r = fp_mul(x, y); break;
+    case 1: r = fp_add(x, y); break;
+    case 2: r = fp_sub(x, y); break;
+    case 3: r = fp_mul_portable(x, y); break;
+    case 4: r = fp_add_portable(x, y); break;
+    default: r = fp_sub_portable(x, y); break;
+  }
+  out[i] = r;
+}
+
+// Exercises madd / add / dbl / to_affine on the device: out[i] = affine( (a_i + b_i) + 2*a_i - b_i ) = 3 * a_i.
+template <class F>
+__global__ void curve_op_kernel(const Affine<F>* a, const Affine<F>* b, Affine<F>* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  xyzz_madd(acc, a[i], false);
+  xyzz_madd(acc, b[i], false);
+  XYZZ<F> d = xyzz_dbl(XYZZ<F>::from_affine(a[i]));
+  xyzz_add(acc, d);
+  xyzz_madd(acc, b[i], true);
+  out[i] = xyzz_to_affine(acc);
+}
+
+template <class P>
+static uint32_t selftest_field(uint64_t seed, uint32_t n) {
+  std::vector<Fp<P>> a(n), b(n);
+  uint64_t s = seed * 0x9E3779B97F4A7C15ull + 99;
+  auto next = [&]() {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  for (uint32_t i = 0; i < n; i++) {
+    for (int k = 0; k < 4; k++) {
+      uint64_t u = next(), v = next();
+      a[i].v[2 * k] = (uint32_t)u; a[i].v[2 * k + 1] = (uint32_t)(u >> 32);
+      b[i].v[2 * k] = (uint32_t)v; b[i].v[2 * k + 1] = (uint32_t)(v >> 32);
+    }
+    a[i].v[7] &= 0x1fffffffu;
+    b[i].v[7] &= 0x1fffffffu;
+  }
+  // edge values: 0, 1, p-1, R mod p
+  if (n >= 8) {
+    a[0] = Fp<P>::zero(); b[0] = Fp<P>::zero();
+    a[1] = Fp<P>::one(); b[1] = Fp<P>::one();
+    a[2] = fp_sub_portable(Fp<P>::zero(), Fp<P>::one()); b[2] = a[2];
+    a[3] = a[2]; b[3] = Fp<P>::one();
+    a[4] = Fp<P>::zero(); a[4].v[0] = 1; b[4] = a[2];
+    a[5] = fp_sub_portable(Fp<P>::modulus(), a[4]); b[5] = a[5];  // p-1 (plain) twice
+    a[6] = a[5]; b[6] = Fp<P>::zero();
+    a[7] = Fp<P>::zero(); b[7] = a[5];
+  }
+  DevBuf da(n * 32), db(n * 32), dout(n * 32);
+  NZCP_CUDA(cudaMemcpy(da.p, a.data(), n * 32, cudaMemcpyHostToDevice));
+  NZCP_CUDA(cudaMemcpy(db.p, b.data(), n * 32, cudaMemcpyHostToDevice));
+  uint32_t bad = 0;
+  std::vector<Fp<P>> out(n);
+  for (int op = 0; op < 6; op++) {
+    field_op_kernel<P><<<div_up(n, 128), 128>>>(op, da.as<Fp<P>>(), db.as<Fp<P>>(), dout.as<Fp<P>>(), n);
+    NZCP_LAUNCH_CHECK();
+    NZCP_CUDA(cudaMemcpy(out.data(), dout.p, n * 32, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) {
+      Fp<P> e = (op % 3 == 0) ? fp_mul_portable(a[i], b[i]) : (op % 3 == 1) ? fp_add_portable(a[i], b[i]) : fp_sub_portable(a[i], b[i]);
+      if (e != out[i]) bad++;
+    }
+  }
+  return bad;
+}
+
+template <class F>
+static uint32_t selftest_curve(const Affine<F>& gen, uint64_t seed, uint32_t n) {
+  std::vector<Affine<F>> a(n), b(n), out(n);
+  XYZZ<F> g = XYZZ<F>::from_affine(gen);
+  XYZZ<F> p = g, q = xyzz_dbl(g);
+  for (uint32_t k = 0; k < (seed & 7); k++) xyzz_add(p, g);
+  for (uint32_t i = 0; i < n; i++) {
+    xyzz_add(p, q);  // distinct multiples of g
+    q = xyzz_dbl(q);
+    a[i] = xyzz_to_affine(p);
+    b[i] = xyzz_to_affine(q);
+  }
+  if (n >= 4) {
+    b[0] = a[0];                                   // madd hits the doubling branch
+    b[1] = Affine<F>{a[1].x, f_neg(a[1].y)};       // madd hits the cancellation branch
+  }
+  DevBuf da(n * sizeof(Affine<F>)), db(n * sizeof(Affine<F>)), dout(n * sizeof(Affine<F>));
+  NZCP_CUDA(cudaMemcpy(da.p, a.data(), n * sizeof(Affine<F>), cudaMemcpyHostToDevice));
+  NZCP_CUDA(cudaMemcpy(db.p, b.data(), n * sizeof(Affine<F>), cudaMemcpyHostToDevice));
+  curve_op_kernel<F><<<div_up(n, 64), 64>>>(da.as<Affine<F>>(), db.as<Affine<F>>(), dout.as<Affine<F>>(), n);
+  NZCP_LAUNCH_CHECK();
+  NZCP_CUDA(cudaMemcpy(out.data(), dout.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost));
+  uint32_t bad = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    XYZZ<F> e = XYZZ<F>::from_affine(a[i]);
+    XYZZ<F> d = xyzz_dbl(e);
+    xyzz_add(e, d);  // 3a
+    Affine<F> ea = xyzz_to_affine(e);
+    if (!(ea.x == out[i].x) || !(ea.y == out[i].y)) bad++;
+  }
+  return bad;
+}
+
+}  // namespace nzcp
+
+using namespace nzcp;
+
+extern "C" {
+
+int nzcp_ntt(uint8_t* data, int log_n, int inverse, int device, float* kernel_ms) {
+  return api_guard([&] {
+    if (!data) throw ApiError(NZCP_E_ARG, "null argument");
+    if (log_n < 1 || log_n > 27) throw ApiError(NZCP_E_ARG, "log_n out of range [1, 27]");
+    use_device(device);
+    size_t n = (size_t)1 << log_n;
+    NttDomain dom;
+    ntt_domain_create(&dom, log_n, 0);
+    struct Guard { NttDomain* d; ~Guard() { ntt_domain_destroy(d); } } g{&dom};
+    DevBuf d(n * 32), tmp(n * 32);
+    NZCP_CUDA(cudaMemcpy(d.p, data, n * 32, cudaMemcpyHostToDevice));
+    Timer t(0);
+    if (inverse) ntt_inverse(dom, d.as<Fr>(), tmp.as<Fr>(), 0); else ntt_forward(dom, d.as<Fr>(), tmp.as<Fr>(), 0);
+    float ms = t.stop();
+    if (kernel_ms) *kernel_ms = ms;
+    NZCP_CUDA(cudaMemcpy(data, d.p, n * 32, cudaMemcpyDeviceToHost));
+  });
+}
+
+int nzcp_ntt_coset(uint8_t* data, int log_n, int batch, int device, float* kernel_ms) {
+  return api_guard([&] {
+    if (!data || batch < 1) throw ApiError(NZCP_E_ARG, "bad argument");
+    if (log_n < 1 || log_n > 27) throw ApiError(NZCP_E_ARG, "log_n out of range [1, 27]");
+    use_device(device);
+    size_t n = (size_t)1 << log_n;
+    NttDomain dom;
+    ntt_domain_create(&dom, log_n, 0);
+    struct Guard { NttDomain* d; ~Guard() { ntt_domain_destroy(d); } } g{&dom};
+    DevBuf d(n * 32 * batch);
+    NZCP_CUDA(cudaMemcpy(d.p, data, n * 32 * batch, cudaMemcpyHostToDevice));
+    Timer t(0);
+    ntt_coset_pipeline(dom, d.as<Fr>(), batch, 0);
+    float ms = t.stop();
+    if (kernel_ms) *kernel_ms = ms;
+    NZCP_CUDA(cudaMemcpy(data, d.p, n * 32 * batch, cudaMemcpyDeviceToHost));
+  });
+}
+
+int nzcp_msm(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int g2, int window_bits, int device,
+             uint8_t* out, float* kernel_ms) {
+  return api_guard([&] {
+    if (!out || (n_points && (!bases || !scalars))) throw ApiError(NZCP_E_ARG, "null argument");
+    use_device(device);
+    size_t bsz = g2 ? 128 : 64;
+    MsmPlan plan;
+    msm_plan_create(&plan, n_points, g2 != 0, window_bits);
+    struct Guard { MsmPlan* p; ~Guard() { msm_plan_destroy(p); } } gd{&plan};
+    DevBuf db(n_points * bsz), ds(n_points * 32);
+    if (n_points) {
+      NZCP_CUDA(cudaMemcpy(db.p, bases, n_points * bsz, cudaMemcpyHostToDevice));
+      NZCP_CUDA(cudaMemcpy(ds.p, scalars, n_points * 32, cudaMemcpyHostToDevice));
+    }
+    Timer t(0);
+    msm_launch(&plan, db.p, ds.as<Fr>(), n_points, 0);
+    float ms = t.stop();
+    if (kernel_ms) *kernel_ms = ms;
+    try {
+      if (g2) g2_to_plain_bytes(msm_finish_g2(&plan), out); else g1_to_plain_bytes(msm_finish_g1(&plan), out);
+    } catch (const std::runtime_error& e) {
+      throw ApiError(NZCP_E_RANGE, e.what());
+    }
+  });
+}
+
+int nzcp_selftest(int device, uint64_t seed, uint32_t n_cases, uint32_t* n_bad) {
+  return api_guard([&] {
+    if (!n_bad || n_cases == 0) throw ApiError(NZCP_E_ARG, "bad argument");
+    use_device(device);
+    uint32_t bad = 0;
+    bad += selftest_field<FrParams>(seed, n_cases);
+    bad += selftest_field<FqParams>(seed + 1, n_cases);
+    uint32_t nc = n_cases > 64 ? 64 : n_cases;
+    bad += selftest_curve<Fq>(g1_generator(), seed, nc);
+    bad += selftest_curve<Fq2>(g2_generator(), seed, nc);
+    *n_bad = bad;
+  });
+}
+
+int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int device) {
+  return api_guard([&] {
+    if (!a || !b || !out) throw ApiError(NZCP_E_ARG, "null argument");
+    if (op < 0 || op > 5 || field < 0 || field > 1) throw ApiError(NZCP_E_ARG, "bad op/field");
+    use_device(device);
+    DevBuf da(n * 32), db(n * 32), dout(n * 32);
+    NZCP_CUDA(cudaMemcpy(da.p, a, n * 32, cudaMemcpyHostToDevice));
+    NZCP_CUDA(cudaMemcpy(db.p, b, n * 32, cudaMemcpyHostToDevice));
+    if (field == 0)
+      field_op_kernel<FrParams><<<div_up(n, 128), 128>>>(op, da.as<Fr>(), db.as<Fr>(), dout.as<Fr>(), n);
+    else
+      field_op_kernel<FqParams><<<div_up(n, 128), 128>>>(op, da.as<Fq>(), db.as<Fq>(), dout.as<Fq>(), n);
+    NZCP_LAUNCH_CHECK();
+    NZCP_CUDA(cudaMemcpy(out, dout.p, n * 32, cudaMemcpyDeviceToHost));
+  });
+}
+
+// ---- host-side hooks: the same __host__ __device__ arithmetic compiled for the CPU.  Used by the no-GPU tests to pin
+// the code the O(1) host glue (finalisation, twiddle tables, synthetic setup) runs, against the Python oracle.
+int nzcp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  return api_guard([&] {
+    if (!a || !b || !out) throw ApiError(NZCP_E_ARG, "null argument");
+    if (op < 0 || op > 2 || field < 0 || field > 1) throw ApiError(NZCP_E_ARG, "bad op/field");
+    for (size_t i = 0; i < n; i++) {
+      if (field == 0) {
+        Fr x = fp_from_bytes_plain<FrParams>(a + 32 * i), y = fp_from_bytes_plain<FrParams>(b + 32 * i);
+        Fr r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
+        fp_to_bytes(r, out + 32 * i);
+      } else {
+        Fq x = fp_from_bytes_plain<FqParams>(a + 32 * i), y = fp_from_bytes_plain<FqParams>(b + 32 * i);
+        Fq r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
+        fp_to_bytes(r, out + 32 * i);
+      }
+    }
+  });
+}
+
+int nzcp_host_scalar_mul(int g2, const uint8_t* base_mont, const uint8_t* scalar, uint8_t* out_plain) {
+  return api_guard([&] {
+    if (!scalar || !out_plain) throw ApiError(NZCP_E_ARG, "null argument");
+    Fr k = fp_from_bytes_plain<FrParams>(scalar);
+    if (g2) {
+      G2Affine b = g2_generator();
+      if (base_mont) memcpy(&b, base_mont, 128);
+      g2_to_plain_bytes(xyzz_mul(G2XYZZ::from_affine(b), k.v), out_plain);
+    } else {
+      G1Affine b = g1_generator();
+      if (base_mont) memcpy(&b, base_mont, 64);
+      g1_to_plain_bytes(xyzz_mul(G1XYZZ::from_affine(b), k.v), out_plain);
+    }
+  });
+}
+
+int nzcp_host_root_of_unity(int k, uint8_t* out_plain) {
+  return api_guard([&] {
+    if (!out_plain || k < 0 || k > 28) throw ApiError(NZCP_E_ARG, "bad argument");
+    fp_to_bytes(fp_from_mont(host_fr_root(k)), out_plain);
+  });
+}
+
+}  // extern "C"
