@@ -1,0 +1,263 @@
+"""Object wrappers over the C ABI (include/nzcp_prover.h): Zkey, Prover, and the standalone NTT / MSM calls.
+
+This is the layer a Node N-API addon would sit at; groth16.py puts the snarkjs-shaped surface on
+top of it.  Everything computes on the GPU through libnzcp_prover.so; nothing here falls back to the CPU.
+"""
+import ctypes as C
+
+from . import _lib
+from ._lib import NzcpError, Proof, ProveDebug, ZkeyInfo, addr, check
+
+STAGE_NAMES = ("upload", "r1cs_eval", "ntt_join", "msm_a", "msm_b1", "msm_b2", "msm_c", "msm_h")
+
+
+def _as_bytes_like(x):
+    """Path | bytes-like | {"type": "mem", "data": ...} (fastfile convention) -> bytes-like."""
+    if isinstance(x, dict) and x.get("type") == "mem":
+        return x["data"]
+    if isinstance(x, str) or hasattr(x, "__fspath__"):
+        with open(x, "rb") as f:
+            return f.read()
+    return x
+
+
+def _nbytes(buf):
+    if hasattr(buf, "nbytes"):
+        return int(buf.nbytes)
+    return len(buf)
+
+
+def _scalar32(v):
+    """int | 32 bytes | None -> 32-byte LE or None."""
+    if v is None:
+        return None
+    if isinstance(v, int):
+        return int(v).to_bytes(32, "little")
+    b = bytes(v)
+    if len(b) != 32:
+        raise NzcpError(_lib.NZCP_E_ARG, "blinding scalar must be 32 bytes")
+    return b
+
+
+def device_count():
+    return _lib.load().nzcp_device_count()
+
+
+class Zkey:
+    """A proving key resident on one GPU (sections 4-9 parsed and uploaded once)."""
+
+    def __init__(self, zkey, device=0):
+        lib = _lib.load()
+        data = _as_bytes_like(zkey)
+        h = C.c_void_p()
+        check(lib.nzcp_zkey_load(addr(data), _nbytes(data), int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        inf = ZkeyInfo()
+        check(lib.nzcp_zkey_info_get(self._h, C.byref(inf)))
+        self.n_vars, self.n_public, self.domain_size = inf.n_vars, inf.n_public, inf.domain_size
+        self.power, self.n_coefs, self.device_bytes = inf.power, inf.n_coefs, inf.device_bytes
+        self._info = inf
+
+    def header_points(self):
+        """alpha1, beta1, delta1 (64 B) and beta2, gamma2, delta2 (128 B): plain affine LE bytes."""
+        i = self._info
+        return {"alpha1": bytes(i.alpha1), "beta1": bytes(i.beta1), "delta1": bytes(i.delta1),
+                "beta2": bytes(i.beta2), "gamma2": bytes(i.gamma2), "delta2": bytes(i.delta2)}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().nzcp_zkey_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Prover:
+    """Work buffers + streams for proofs against one Zkey.  One in-flight proof per Prover."""
+
+    def __init__(self, zkey):
+        self.zkey = zkey
+        h = C.c_void_p()
+        check(_lib.load().nzcp_prover_create(zkey._h, C.byref(h)))
+        self._h = h
+
+    def _finish(self, proof, dbg, want_h, hbuf):
+        out = {"proof": bytes(proof.pi_a) + bytes(proof.pi_b) + bytes(proof.pi_c)}
+        if dbg is not None:
+            out.update(msm_a=bytes(dbg.msm_a), msm_b1=bytes(dbg.msm_b1), msm_b2=bytes(dbg.msm_b2),
+                       msm_c=bytes(dbg.msm_c), msm_h=bytes(dbg.msm_h),
+                       stage_ms=dict(zip(STAGE_NAMES, [float(x) for x in dbg.stage_ms])))
+            if want_h:
+                out["h"] = bytes(hbuf)
+        return out
+
+    def _dbg(self, debug, want_h):
+        if not debug and not want_h:
+            return None, None, None
+        dbg = ProveDebug()
+        hbuf = None
+        if want_h:
+            hbuf = bytearray(self.zkey.domain_size * 32)
+            dbg.h_scalars = addr(hbuf)
+        return dbg, hbuf, C.byref(dbg)
+
+    def prove(self, wtns, r=None, s=None, debug=False, want_h=False):
+        """`wtns`: a complete .wtns image (bytes-like or path).  -> dict(proof=256 bytes, [msm_*, stage_ms, h])."""
+        data = _as_bytes_like(wtns)
+        proof = Proof()
+        dbg, hbuf, ref = self._dbg(debug, want_h)
+        rb, sb = _scalar32(r), _scalar32(s)
+        check(_lib.load().nzcp_prove(self._h, addr(data), _nbytes(data), addr(rb), addr(sb), C.byref(proof), ref))
+        return self._finish(proof, dbg, want_h, hbuf)
+
+    def prove_witness(self, witness, n_witness, r=None, s=None, debug=False, want_h=False):
+        """`witness`: n_witness x 32-byte LE plain values in host memory (section 2 of a .wtns)."""
+        proof = Proof()
+        dbg, hbuf, ref = self._dbg(debug, want_h)
+        rb, sb = _scalar32(r), _scalar32(s)
+        check(_lib.load().nzcp_prove_witness(self._h, addr(witness), int(n_witness), addr(rb), addr(sb),
+                                             C.byref(proof), ref))
+        return self._finish(proof, dbg, want_h, hbuf)
+
+    def prove_device(self, d_witness, r=None, s=None, debug=False):
+        """`d_witness`: device pointer (int or torch tensor) to n_vars x 32 B already in HBM."""
+        proof = Proof()
+        dbg, hbuf, ref = self._dbg(debug, False)
+        rb, sb = _scalar32(r), _scalar32(s)
+        check(_lib.load().nzcp_prove_device(self._h, addr(d_witness), addr(rb), addr(sb), C.byref(proof), ref))
+        return self._finish(proof, dbg, False, hbuf)
+
+    def witness_buffer(self):
+        return _lib.load().nzcp_prover_witness_buffer(self._h)
+
+    def launch_count(self):
+        return int(_lib.load().nzcp_prover_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().nzcp_prover_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ standalone kernels
+def ntt(data, log_n, inverse=False, device=0):
+    """In-place natural-order NTT/iNTT of 2^log_n Montgomery-form Fr values held in a writable buffer.
+    Returns kernel milliseconds."""
+    ms = C.c_float()
+    check(_lib.load().nzcp_ntt(addr(data), int(log_n), int(bool(inverse)), int(device), C.byref(ms)))
+    return ms.value
+
+
+def ntt_coset(data, log_n, batch=1, device=0):
+    ms = C.c_float()
+    check(_lib.load().nzcp_ntt_coset(addr(data), int(log_n), int(batch), int(device), C.byref(ms)))
+    return ms.value
+
+
+def msm(bases, scalars, n_points, g2=False, window_bits=0, device=0):
+    """-> (plain affine point bytes: 64 for G1 / 128 for G2, kernel ms)."""
+    out = bytearray(128 if g2 else 64)
+    ms = C.c_float()
+    check(_lib.load().nzcp_msm(addr(bases), addr(scalars), int(n_points), int(bool(g2)), int(window_bits), int(device),
+                               addr(out), C.byref(ms)))
+    return bytes(out), ms.value
+
+
+def selftest(device=0, seed=1, n_cases=4096):
+    bad = C.c_uint32()
+    check(_lib.load().nzcp_selftest(int(device), int(seed), int(n_cases), C.byref(bad)))
+    return bad.value
+
+
+def field_op(field, op, a, b, n, device=0):
+    out = bytearray(32 * n)
+    check(_lib.load().nzcp_field_op(int(field), int(op), addr(a), addr(b), addr(out), int(n), int(device)))
+    return bytes(out)
+
+
+def host_field_op(field, op, a, b, n):
+    out = bytearray(32 * n)
+    check(_lib.load().nzcp_host_field_op(int(field), int(op), addr(a), addr(b), addr(out), int(n)))
+    return bytes(out)
+
+
+def host_scalar_mul(g2, base_mont, scalar):
+    out = bytearray(128 if g2 else 64)
+    sb = _scalar32(scalar)
+    check(_lib.load().nzcp_host_scalar_mul(int(bool(g2)), addr(base_mont), addr(sb), addr(out)))
+    return bytes(out)
+
+
+def host_root_of_unity(k):
+    out = bytearray(32)
+    check(_lib.load().nzcp_host_root_of_unity(int(k), addr(out)))
+    return int.from_bytes(out, "little")
+
+
+# ------------------------------------------------------------------------------------------------ synthetic circuits
+class SynthCircuit:
+    """Random forward-solvable R1CS of the NZCP shape + Groth16 setup from explicit toxic waste (GPU)."""
+
+    def __init__(self, seed, n_constraints, n_public, n_free):
+        h = C.c_void_p()
+        check(_lib.load().nzcp_synth_create(int(seed), int(n_constraints), int(n_public), int(n_free), C.byref(h)))
+        self._h = h
+        nv, nc, npub, dom = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        ncoef = C.c_uint64()
+        check(_lib.load().nzcp_synth_dims(h, C.byref(nv), C.byref(nc), C.byref(npub), C.byref(dom), C.byref(ncoef)))
+        self.n_vars, self.n_constraints, self.n_public = nv.value, nc.value, npub.value
+        self.domain_size, self.n_coefs = dom.value, ncoef.value
+
+    def zkey(self, toxic, device=0):
+        """toxic: 5 ints (tau, alpha, beta, gamma, delta) -> bytearray with the .zkey image."""
+        lib = _lib.load()
+        tb = b"".join(int(t).to_bytes(32, "little") for t in toxic)
+        out = bytearray(lib.nzcp_synth_zkey_size(self._h))
+        check(lib.nzcp_synth_write_zkey(self._h, addr(tb), int(device), addr(out), len(out)))
+        return out
+
+    def r1cs(self):
+        lib = _lib.load()
+        out = bytearray(lib.nzcp_synth_r1cs_size(self._h))
+        check(lib.nzcp_synth_write_r1cs(self._h, addr(out), len(out)))
+        return out
+
+    def wtns(self, witness_seed):
+        lib = _lib.load()
+        out = bytearray(lib.nzcp_synth_wtns_size(self._h))
+        check(lib.nzcp_synth_write_wtns(self._h, int(witness_seed), addr(out), len(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().nzcp_synth_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
