@@ -113,6 +113,10 @@ int nzcp_selftest(int device, uint64_t seed, uint32_t n_cases, uint32_t* n_bad);
  * field 0 = Fr, 1 = Fq. */
 int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int device);
 
+/* Integer-pipe microbenchmark (the MSM / NTT roofline denominator): out[0] = mad.wide.u32 per second, out[1] = mad.lo.u32
+ * per second, out[2] = dependent-chain Fq Montgomery products per second, out[3] = SM count. */
+int nzcp_intpipe_bench(int device, int iters, double out[4]);
+
 /* ---- host hooks: the library's __host__ __device__ arithmetic compiled for the CPU (what the O(1) host glue runs).
  * Test-only; they let the no-GPU suite pin that code against the oracle.  op: 0 mul, 1 add, 2 sub. */
 int nzcp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "nzcp_msm": (C.c_int, [_U8P, _U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, _U8P, C.POINTER(C.c_float)]),
     "nzcp_selftest": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
     "nzcp_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t, C.c_int]),
+    "nzcp_intpipe_bench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "nzcp_host_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t]),
     "nzcp_host_scalar_mul": (C.c_int, [C.c_int, _U8P, _U8P, _U8P]),
     "nzcp_host_root_of_unity": (C.c_int, [C.c_int, _U8P]),

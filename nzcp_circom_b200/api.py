@@ -198,6 +198,13 @@ def field_op(field, op, a, b, n, device=0):
     return bytes(out)
 
 
+def intpipe_bench(device=0, iters=4096):
+    """-> dict(imad_wide_per_s, imad_lo_per_s, fq_mul_per_s, sm_count): the integer-pipe roofline denominators."""
+    out = (C.c_double * 4)()
+    check(_lib.load().nzcp_intpipe_bench(int(device), int(iters), out))
+    return {"imad_wide_per_s": out[0], "imad_lo_per_s": out[1], "fq_mul_per_s": out[2], "sm_count": int(out[3])}
+
+
 def host_field_op(field, op, a, b, n):
     out = bytearray(32 * n)
     check(_lib.load().nzcp_host_field_op(int(field), int(op), addr(a), addr(b), addr(out), int(n)))

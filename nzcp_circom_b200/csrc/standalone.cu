@@ -151,11 +151,87 @@ static uint32_t selftest_curve(const Affine<F>& gen, uint64_t seed, uint32_t n) 
   return bad;
 }
 
+
+// ------------------------------------------------------------------------------------------------ integer-pipe peak
+// Microbenchmarks behind the MSM / NTT roofline denominator (MEASURED_PEAKS.json has no integer-pipe figure):
+//   mode 0: independent mad.wide.u32 chains (IMAD.WIDE.U32), the instruction the Montgomery product is made of
+//   mode 1: independent mad.lo.u32 chains (IMAD)
+//   mode 2: fp_mul<Fq> chains, 2 independent products per thread (what a kernel that did nothing else would reach)
+__global__ void __launch_bounds__(256) intpipe_kernel(int mode, int iters, uint32_t seed, uint32_t* sink) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 0) {
+    unsigned long long a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+    uint32_t x = seed | 1, y = seed + t;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\t"
+                     "mad.wide.u32 %3, %8, %9, %3;\n\tmad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
+                     "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                     : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7)
+                     : "r"(x), "r"(y));
+      }
+    }
+    unsigned long long s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (s == 0x123456789ull) sink[0] = (uint32_t)s;
+  } else if (mode == 1) {
+    uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+    uint32_t x = seed | 1, y = seed + t;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        asm volatile("mad.lo.u32 %0, %8, %9, %0;\n\tmad.lo.u32 %1, %8, %9, %1;\n\tmad.lo.u32 %2, %8, %9, %2;\n\t"
+                     "mad.lo.u32 %3, %8, %9, %3;\n\tmad.lo.u32 %4, %8, %9, %4;\n\tmad.lo.u32 %5, %8, %9, %5;\n\t"
+                     "mad.lo.u32 %6, %8, %9, %6;\n\tmad.lo.u32 %7, %8, %9, %7;"
+                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                     : "r"(x), "r"(y));
+      }
+    }
+    uint32_t s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (s == 0x12345678u) sink[0] = s;
+  } else {
+    Fq a = Fq::one(), b = Fq::r2(), c = Fq::one();
+    a.v[0] ^= t & 0xffff;
+    c.v[1] ^= (seed + t) & 0xffff;
+    for (int i = 0; i < iters; i++) {
+      a = fp_mul(a, b);
+      c = fp_mul(c, b);
+    }
+    if ((a.v[0] ^ c.v[0]) == 0x12345678u) sink[0] = a.v[1];
+  }
+}
+
 }  // namespace nzcp
 
 using namespace nzcp;
 
 extern "C" {
+
+int nzcp_intpipe_bench(int device, int iters, double out[4]) {
+  return api_guard([&] {
+    if (!out || iters < 1) throw ApiError(NZCP_E_ARG, "bad argument");
+    use_device(device);
+    cudaDeviceProp prop;
+    NZCP_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevBuf sink(64);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    const double per_thread[3] = {64.0 * iters, 64.0 * iters, 2.0 * iters};
+    for (int mode = 0; mode < 3; mode++) {
+      int it = mode == 2 ? (iters / 16 > 0 ? iters / 16 : 1) : iters;
+      float best = 1e30f;
+      for (int rep = 0; rep < 4; rep++) {
+        Timer t(0);
+        intpipe_kernel<<<blocks, threads>>>(mode, it, 12345u + rep, sink.as<uint32_t>());
+        NZCP_LAUNCH_CHECK();
+        float ms = t.stop();
+        if (rep && ms < best) best = ms;
+      }
+      double ops = (mode == 2 ? 2.0 * it : per_thread[mode]) * (double)blocks * threads;
+      out[mode] = ops / (best * 1e-3);
+    }
+    out[3] = (double)prop.multiProcessorCount;
+  });
+}
 
 int nzcp_ntt(uint8_t* data, int log_n, int inverse, int device, float* kernel_ms) {
   return api_guard([&] {
