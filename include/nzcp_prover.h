@@ -67,7 +67,11 @@ typedef struct nzcp_prove_debug {
   uint8_t msm_h[64];
   uint8_t* h_scalars;      /* optional: caller buffer of domain_size*32 bytes receiving the joinABC output, or NULL */
   float stage_ms[8];       /* device time: 0 upload, 1 r1cs eval, 2 ntt pipeline+join, 3 msm A, 4 msm B1, 5 msm B2, */
-                           /*              6 msm C, 7 msm H                                                         */
+                           /*              6 msm C, 7 msm H (bucket sort of h included)                             */
+  float sort_ms[2];        /* bucket sort of the witness (shared by A, B1, B2, C) / of the h scalars                */
+  float accumulate_ms[5];  /* the bucket-accumulate kernel alone (CUDA events on its stream): A, B1, B2, C, H       */
+  uint32_t n_entries[2];   /* non-zero signed digits (= mixed additions per MSM): witness, h                        */
+  float total_ms;          /* first event to end of the H MSM on the main stream                                    */
 } nzcp_prove_debug;
 
 const char* nzcp_last_error(void);
@@ -113,9 +117,11 @@ int nzcp_selftest(int device, uint64_t seed, uint32_t n_cases, uint32_t* n_bad);
  * field 0 = Fr, 1 = Fq. */
 int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int device);
 
-/* Integer-pipe microbenchmark (the MSM / NTT roofline denominator): out[0] = mad.wide.u32 per second, out[1] = mad.lo.u32
- * per second, out[2] = dependent-chain Fq Montgomery products per second, out[3] = SM count. */
+/* Integer-pipe microbenchmark (the MSM / NTT roofline denominator): out[0] = IMAD.WIDE.U32 (32x32->64 multiply-add) per
+ * second, out[1] = 32-bit IMAD per second, out[2] = dependent-chain Fq Montgomery products per second, out[3] = SM count. */
 int nzcp_intpipe_bench(int device, int iters, double out[4]);
+/* Diagnostic: rates of the carry-chain variants (modes 0..8 of csrc/standalone.cu intpipe_kernel), out[9] = SM count. */
+int nzcp_intpipe_modes(int device, int iters, double out[10]);
 
 /* ---- host hooks: the library's __host__ __device__ arithmetic compiled for the CPU (what the O(1) host glue runs).
  * Test-only; they let the no-GPU suite pin that code against the oracle.  op: 0 mul, 1 add, 2 sub. */

@@ -37,7 +37,8 @@ class Proof(C.Structure):
 class ProveDebug(C.Structure):
     _fields_ = [("msm_a", C.c_uint8 * 64), ("msm_b1", C.c_uint8 * 64), ("msm_b2", C.c_uint8 * 128),
                 ("msm_c", C.c_uint8 * 64), ("msm_h", C.c_uint8 * 64), ("h_scalars", C.c_void_p),
-                ("stage_ms", C.c_float * 8)]
+                ("stage_ms", C.c_float * 8), ("sort_ms", C.c_float * 2), ("accumulate_ms", C.c_float * 5),
+                ("n_entries", C.c_uint32 * 2), ("total_ms", C.c_float)]
 
 
 # every symbol include/nzcp_prover.h declares: name -> (restype, argtypes)
@@ -61,6 +62,7 @@ SIGNATURES = {
     "nzcp_msm": (C.c_int, [_U8P, _U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, _U8P, C.POINTER(C.c_float)]),
     "nzcp_selftest": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
     "nzcp_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t, C.c_int]),
+    "nzcp_intpipe_modes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "nzcp_intpipe_bench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "nzcp_host_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t]),
     "nzcp_host_scalar_mul": (C.c_int, [C.c_int, _U8P, _U8P, _U8P]),

@@ -97,7 +97,11 @@ class Prover:
         if dbg is not None:
             out.update(msm_a=bytes(dbg.msm_a), msm_b1=bytes(dbg.msm_b1), msm_b2=bytes(dbg.msm_b2),
                        msm_c=bytes(dbg.msm_c), msm_h=bytes(dbg.msm_h),
-                       stage_ms=dict(zip(STAGE_NAMES, [float(x) for x in dbg.stage_ms])))
+                       stage_ms=dict(zip(STAGE_NAMES, [float(x) for x in dbg.stage_ms])),
+                       sort_ms={"witness": float(dbg.sort_ms[0]), "h": float(dbg.sort_ms[1])},
+                       accumulate_ms=dict(zip(("a", "b1", "b2", "c", "h"), [float(x) for x in dbg.accumulate_ms])),
+                       n_entries={"witness": int(dbg.n_entries[0]), "h": int(dbg.n_entries[1])},
+                       total_ms=float(dbg.total_ms))
             if want_h:
                 out["h"] = bytes(hbuf)
         return out
@@ -162,6 +166,51 @@ class Prover:
             pass
 
 
+class ProverPool:
+    """Several Provers on one resident Zkey, driven from host threads so that the latency-bound tail of one proof (bucket
+    reduction trees, host finalisation) overlaps the integer-pipe-bound kernels of the next.  ctypes drops the GIL inside
+    the library calls.  Proof i is independent of proof j: this is the batch mode of SURVEY.md 8e on ONE GPU."""
+
+    def __init__(self, zkey, n_provers=2):
+        from concurrent.futures import ThreadPoolExecutor
+        self.zkey = zkey
+        self.provers = [Prover(zkey) for _ in range(max(1, int(n_provers)))]
+        self._pool = ThreadPoolExecutor(max_workers=len(self.provers))
+
+    def _run(self, method, items, r, s, kw):
+        k = len(self.provers)
+
+        def work(j):
+            pr = self.provers[j]
+            return [(i, getattr(pr, method)(*items[i], r=r, s=s, **kw)) for i in range(j, len(items), k)]
+        out = [None] * len(items)
+        for fut in [self._pool.submit(work, j) for j in range(k)]:
+            for i, res in fut.result():
+                out[i] = res
+        return out
+
+    def prove_many(self, wtns_list, r=None, s=None, **kw):
+        """.wtns images (host memory) -> list of result dicts, in order."""
+        return self._run("prove", [(w,) for w in wtns_list], r, s, kw)
+
+    def prove_device_many(self, d_witness_list, r=None, s=None, **kw):
+        return self._run("prove_device", [(d,) for d in d_witness_list], r, s, kw)
+
+    def launch_count(self):
+        return self.provers[0].launch_count()
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for p in self.provers:
+            p.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 # ------------------------------------------------------------------------------------------------ standalone kernels
 def ntt(data, log_n, inverse=False, device=0):
     """In-place natural-order NTT/iNTT of 2^log_n Montgomery-form Fr values held in a writable buffer.
@@ -203,6 +252,14 @@ def intpipe_bench(device=0, iters=4096):
     out = (C.c_double * 4)()
     check(_lib.load().nzcp_intpipe_bench(int(device), int(iters), out))
     return {"imad_wide_per_s": out[0], "imad_lo_per_s": out[1], "fq_mul_per_s": out[2], "sm_count": int(out[3])}
+
+
+def intpipe_modes(device=0, iters=4096):
+    out = (C.c_double * 10)()
+    check(_lib.load().nzcp_intpipe_modes(int(device), int(iters), out))
+    names = ("mad_wide", "mad_lo", "fq_mul", "chain2_wide", "chain4_wide", "chain8_wide", "chain2_plus_addc", "addc_only",
+             "mad_wide_plus_2addc")
+    return dict(zip(names, list(out)[:9]))
 
 
 def host_field_op(field, op, a, b, n):

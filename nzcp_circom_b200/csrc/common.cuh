@@ -68,38 +68,69 @@ struct R1csDevice {
 void r1cs_eval(const R1csDevice& m, const Fr* witness, Fr* abc, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------- MSM (msm.cu)
-struct MsmPlan {
-  size_t n_points = 0;
-  int c = 0;          // window bits (signed digits)
-  int n_windows = 0;
-  size_t n_buckets = 0;  // per window = 2^(c-1)
+// Precomputed window table of one base section (built once per proving key; the bases never change between proofs):
+//   pts[w * n_points + i] = 2^(c*w) * P_i   affine Montgomery, (0,0) = infinity
+// so that all windows of a scalar feed ONE bucket set and the Horner pass over windows disappears.
+struct MsmTable {
+  void* pts = nullptr;
+  size_t n_points = 0;   // including pad_front leading infinity points
+  int c = 0, n_windows = 0;
   bool g2 = false;
-  // device scratch
-  uint32_t* counts = nullptr;    // n_windows * n_buckets (+1)
+  size_t bytes = 0;
+};
+int msm_pick_window(size_t n_points);
+int msm_num_windows(int c);
+// d_bases: device array of n_src affine points; the table gets pad_front infinity points in front of them.
+void msm_table_create(MsmTable* t, const void* d_bases, size_t n_src, size_t pad_front, bool g2, int c, cudaStream_t st);
+void msm_table_destroy(MsmTable* t);
+
+// Bucket sort of one scalar vector: signed c-bit digits -> (table index | sign) entries grouped by bucket, cut into
+// tasks of <= kTaskLen entries.  Shared by every MSM that uses the same scalars (A, B1, B2, C all use the witness).
+struct MsmSort {
+  size_t n_points = 0;
+  int c = 0, n_windows = 0;
+  size_t n_buckets = 0;     // 2^(c-1)
+  uint32_t* counts = nullptr;
   uint32_t* offsets = nullptr;
   uint32_t* cursors = nullptr;
-  uint32_t* entries = nullptr;   // n_windows * n_points
-  uint32_t* task_cnt = nullptr;  // per bucket
-  uint32_t* task_off = nullptr;  // per bucket (+1)
-  uint2* tasks = nullptr;        // (start, len)
-  void* partial = nullptr;       // XYZZ per task
-  void* buckets = nullptr;       // XYZZ per bucket
-  void* lvl_a[2] = {nullptr, nullptr};  // ping-pong level arrays (A sums)
-  void* lvl_r[2] = {nullptr, nullptr};  // ping-pong level arrays (R weighted sums)
-  uint32_t* heavy_list = nullptr;
-  uint32_t* flags = nullptr;     // [0] heavy count, [1] error flag (scalar >= r), [2] total tasks
-  void* window_out = nullptr;    // device: n_windows XYZZ
-  void* window_host = nullptr;   // pinned host mirror
+  uint32_t* bcount = nullptr;      // entries per bucket
+  uint32_t* block_sums = nullptr;  // scratch of the multi-block scan
+  uint32_t* entries = nullptr;
+  uint32_t* task_off = nullptr;
+  uint2* tasks = nullptr;
+  uint32_t* flags = nullptr;      // [1] error flags, [2] total tasks, [3] total entries
+  uint32_t* flags_host = nullptr; // pinned mirror
   size_t max_tasks = 0;
   size_t scratch_bytes = 0;
 };
-int msm_pick_window(size_t n_points);
-void msm_plan_create(MsmPlan* p, size_t n_points, bool g2, int c_override);
-void msm_plan_destroy(MsmPlan* p);
-// Launch all kernels of one MSM on `st`; leaves per-window sums in p->window_host after the stream drains.
-void msm_launch(MsmPlan* p, const void* bases, const Fr* scalars, size_t n_points, cudaStream_t st);
-// Host: Horner over the window sums (after stream sync).  Throws if the device flagged a scalar >= r.
-G1XYZZ msm_finish_g1(const MsmPlan* p);
-G2XYZZ msm_finish_g2(const MsmPlan* p);
+void msm_sort_create(MsmSort* s, size_t n_points, int c);
+void msm_sort_destroy(MsmSort* s);
+void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_t st);
+// After the stream drained: throws if the device flagged a scalar >= r.  Returns the number of non-zero digits.
+uint32_t msm_sort_check(const MsmSort* s);
+
+// One MSM against a sorted scalar vector: accumulate -> combine -> bucket reduction.
+struct MsmRun {
+  bool g2 = false;
+  void* partial = nullptr;
+  void* buckets = nullptr;
+  void* lvl_a[2] = {nullptr, nullptr};
+  void* lvl_r[2] = {nullptr, nullptr};
+  uint32_t* heavy_list = nullptr;
+  uint32_t* heavy_count = nullptr;   // [0] heavy buckets, [1] heavy chunks
+  uint32_t* chunk_cnt = nullptr;
+  uint32_t* chunk_off = nullptr;
+  void* chunk_partial = nullptr;
+  void* out = nullptr;        // device: A_top, R_top
+  void* out_host = nullptr;   // pinned
+  cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;  // around the accumulate kernel (roofline timing)
+  size_t scratch_bytes = 0;
+};
+void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2);
+void msm_run_destroy(MsmRun* r);
+void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaStream_t st);
+G1XYZZ msm_run_finish_g1(const MsmRun* r);
+G2XYZZ msm_run_finish_g2(const MsmRun* r);
+float msm_run_accumulate_ms(const MsmRun* r);
 
 }  // namespace nzcp

@@ -1,4 +1,5 @@
-// Multi-scalar multiplication sum_i s_i * P_i over BN254 G1 and G2 -- signed-digit Pippenger, bucket method.
+// Multi-scalar multiplication sum_i s_i * P_i over BN254 G1 and G2 -- signed-digit Pippenger on precomputed
+// window tables.
 //
 // Replaces (upstream, not vendored: yarn.lock:408-416, 1132-1135) ffjavascript src/engine_multiexp.js
 // (G1.multiExpAffine / G2.multiExpAffine: window size pTSizes[log2 N], one _multiExpChunk task per window and point
@@ -7,31 +8,47 @@
 // scalars are 32-byte little-endian *plain* integers < r (the witness, or the from-Montgomery h vector).
 // The sum is an exact group element, so its affine form is bit-identical to the reference's.
 //
-// B200 design (one MSM = one stream-ordered chain of launches, no host round trip until the end):
-//   1 digits/count   signed c-bit digits (c = 16 at 2^20: 16 windows x 2^15 buckets); histogram with REDG atomics
-//   2 scan           exclusive prefix sum of the 2^19 bucket counts (single block)
-//   3 scatter        point index | sign<<31 written into its bucket's slot range (sorted-by-bucket entry list)
-//   4 tasks          every bucket is cut into tasks of <= kTaskLen entries so that the 0/1-heavy witness
-//                    distribution (27 % of all points land in one bucket) still load-balances
-//   5 accumulate     one thread per task: XYZZ accumulator in registers, 8M+2S mixed adds, bases gathered by index
-//                    (64 B / 128 B per point, L2-resident at these sizes)
-//   6 combine        sum the tasks of a bucket (a block-wide tree for the few heavy buckets)
-//   7 reduce         sum_v v * B_v per window by a radix-8 tree of running sums (no scalar multiplications)
-//   8 host           Horner over the <= 64 window sums (O(1) group operations, as snarkjs does on its main thread)
+// B200 design.  The bases of a proving key never change, and a B200 has 180 GB of HBM, so every base section is
+// expanded ONCE (at zkey load) into a window table  T[w][i] = 2^(c w) P_i  (16 x the section: 5.6 GB for the NZCP
+// key).  With it  sum_i s_i P_i = sum_{i,w} d_{i,w} T[w][i]  is a single bucket problem: all windows share one set
+// of 2^(c-1) buckets, there is no per-window reduction and no Horner pass.  One MSM is a stream-ordered chain:
+//   sort (once per scalar vector, shared by A / B1 / B2 / C which all use the witness):
+//     1 digits/count   signed c-bit digits (c = 16 at 2^20), histogram over 2^15 buckets
+//     2 scan           exclusive prefix sum of the bucket counts
+//     3 scatter        (w * n + i) | sign << 31 written into the bucket's slot range
+//     4 tasks          every bucket is cut into tasks of <= 64 entries, so the 0/1-heavy witness distribution
+//                      (a quarter of all wires land in bucket "1") still load-balances
+//   run (per base section):
+//     5 accumulate     one thread per task: XYZZ accumulator in registers, 8M+2S mixed adds, table entries gathered
+//                      by index with the next one prefetched into L1 during the current add
+//     6 combine        one warp per bucket sums its tasks (shuffle tree); a block per bucket for the few huge ones
+//     7 reduce         sum_v v * B_v by a radix-32 tree: per group a warp does a suffix scan + tree sum with shuffles
+//     8 host           R_top + A_top, one group addition
 #include "common.cuh"
+
+#ifndef NZCP_G2_ACC_BLOCKS
+#define NZCP_G2_ACC_BLOCKS 3
+#endif
 
 namespace nzcp {
 
-static constexpr int kTaskLen = 64;       // max entries per accumulate task
-static constexpr int kLightTasks = 2;     // buckets with more tasks than this go to the block-wide combine
+static constexpr int kTaskLenMax = 64;     // entries per accumulate task: 8..64, picked on the device from the entry
+static constexpr int kTaskLenMin = 8;      //   count so that the tasks about fill the GPU once (flags[4])
+static constexpr int kTargetTasks = 148 * 640;  // resident accumulate threads of a B200 (G1: 5 blocks of 128 per SM)
+static constexpr int kHeavyTasks = 16;     // buckets with more tasks than this go to the block-wide combine
 static constexpr int kHeavyThreads = 128;
-static constexpr int kGroupLog = 3;       // radix of the bucket-reduction tree
+static constexpr int kHeavyChunk = 512;     // task partials per stage-1 block of the heavy combine
+static constexpr int kGroupLog = 5;        // radix of the bucket-reduction tree (one warp per group)
+static constexpr int kCopiesLog = 4;       // 2^4 private copies of every bucket counter (spreads the L2 atomics)
+static constexpr int kCopies = 1 << kCopiesLog;
+static constexpr int kScanBlock = 1024;    // elements per block of the multi-block scan
 
 struct DigitParams {
-  uint32_t n_points;
+  uint32_t n_points;  // scalars in this launch
+  uint32_t stride;    // points per window of the table the entries index (>= n_points)
   int c;
   int n_windows;
-  uint32_t n_buckets;  // per window
+  uint32_t n_buckets;
 };
 
 __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, int pos, int c) {
@@ -43,21 +60,40 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, int pos, int 
   return (uint32_t)v & ((1u << c) - 1);
 }
 
+// ------------------------------------------------------------------------------------------------ window table
+template <class F>
+__global__ void __launch_bounds__(128)
+msm_table_kernel(const Affine<F>* __restrict__ src, size_t n_src, size_t pad_front, Affine<F>* __restrict__ table,
+                 size_t n_points, int c, int n_windows) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  Affine<F> p = i < pad_front ? Affine<F>::inf() : src[i - pad_front];
+  table[i] = p;
+  for (int w = 1; w < n_windows; w++) {
+    if (!p.is_inf()) {
+      XYZZ<F> acc = xyzz_dbl_affine(p);
+      for (int k = 1; k < c; k++) acc = xyzz_dbl(acc);
+      p = xyzz_to_affine(acc);
+    }
+    table[(size_t)w * n_points + i] = p;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sort
 // COUNT pass: histogram.  SCATTER pass: cursors start at the bucket offsets; write the entry list.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 msm_digits_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __restrict__ counts_or_cursors,
                   uint32_t* __restrict__ entries, uint32_t* __restrict__ flags) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_points) return;
-  uint32_t s[8];
-  {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // No early exits: every lane of the warp takes part in the __match_any_sync below (inactive ones with zero digits).
+  bool valid = i < p.n_points;
+  uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (valid) {
     const uint4* q = reinterpret_cast<const uint4*>(scalars + i);
     uint4 a = __ldg(q), b = __ldg(q + 1);
     s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
     s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-  }
-  if (!SCATTER) {
     // scalars must be canonical (< r); anything else is a malformed witness
     bool ge = true;
 #pragma unroll
@@ -69,11 +105,16 @@ msm_digits_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __res
       }
     }
     if (ge) {
-      atomicOr(&flags[1], 1u);
-      return;
+      if (!SCATTER) atomicOr(&flags[1], 1u);
+#pragma unroll
+      for (int k = 0; k < 8; k++) s[k] = 0;
     }
   }
-  if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
+  // Counter (d-1) * kCopies + copy: a bucket's sub-ranges stay adjacent, so its entries are still one contiguous run.
+  // Lanes of a warp that hit the same counter (the 0/1-heavy witness: digit 1 in window 0) are merged into one atomic.
+  const uint32_t copy = blockIdx.x & (kCopies - 1);
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned active = 0xffffffffu;
   uint32_t carry = 0;
   for (int w = 0; w < p.n_windows; w++) {
     uint32_t d = scalar_bits(s, w * p.c, p.c) + carry;
@@ -85,31 +126,86 @@ msm_digits_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __res
     } else {
       carry = 0;
     }
-    if (d) {
-      uint32_t b = (uint32_t)w * p.n_buckets + (d - 1);
-      if (SCATTER) {
-        uint32_t pos = atomicAdd(&counts_or_cursors[b], 1u);
-        entries[pos] = i | (neg << 31);
-      } else {
-        atomicAdd(&counts_or_cursors[b], 1u);
-      }
-    }
+    const uint32_t key = d ? d : 0x80000000u + lane;     // zero digits: singleton groups, no atomic
+    const unsigned peers = __match_any_sync(active, key);
+    const uint32_t leader = __ffs(peers) - 1;
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+    uint32_t base = 0;
+    if (d && lane == leader) base = atomicAdd(&counts_or_cursors[(d - 1) * kCopies + copy], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    if (SCATTER && d) entries[base + rank] = ((uint32_t)w * p.stride + i) | (neg << 31);
   }
   if (!SCATTER && carry) atomicOr(&flags[1], 2u);
 }
 
-// Single-block exclusive scan: out[i] = sum_{j<i} f(in[j]), out[n] = total.  f = identity or ceil(x / kTaskLen).
+// Multi-block exclusive scan of the n_buckets * kCopies counters (3 launches: block sums, scan of the sums, rescan).
+__global__ void __launch_bounds__(256) msm_scan_sums_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ sums, uint32_t n) {
+  __shared__ uint32_t sh[8];
+  uint32_t base = blockIdx.x * kScanBlock;
+  uint32_t acc = 0;
+  for (uint32_t i = threadIdx.x; i < kScanBlock; i += 256)
+    if (base + i < n) acc += in[base + i];
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int k = 0; k < 8; k++) t += sh[k];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// out/out2[i] = exclusive prefix of in[] (out2 may be null); block_off = exclusive scan of the block sums.
+__global__ void __launch_bounds__(256)
+msm_scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ block_off, uint32_t* __restrict__ out,
+                      uint32_t* __restrict__ out2, uint32_t n) {
+  __shared__ uint32_t sh[256];
+  const uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * 4;
+  uint32_t v[4], acc = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    acc += v[k];
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    uint32_t t = threadIdx.x >= (uint32_t)off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = block_off[blockIdx.x] + (threadIdx.x ? sh[threadIdx.x - 1] : 0);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (base + k < n) {
+      out[base + k] = run;
+      if (out2) out2[base + k] = run;
+    }
+    run += v[k];
+  }
+}
+
+// Single-block exclusive scan: out[i] = sum_{j<i} f(in[j]), out[n] = total.  f = identity or ceil(x / task_len).
+// TASKS mode first picks the task length from the entry total in flags[3] and publishes it in flags[4].
 template <bool TASKS>
 __global__ void __launch_bounds__(1024)
-msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ total) {
+msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ total,
+                uint32_t* __restrict__ flags) {
   __shared__ uint32_t sums[1024];
+  uint32_t tl = kTaskLenMax;
+  if (TASKS) {
+    uint32_t per_thread = flags[3] / kTargetTasks;
+    while (tl > (uint32_t)kTaskLenMin && tl > per_thread) tl >>= 1;
+    if (threadIdx.x == 0) flags[4] = tl;
+  }
   uint32_t per = (n + 1023) / 1024;
   uint32_t b = threadIdx.x * per;
   uint32_t e = b + per < n ? b + per : n;
   uint32_t acc = 0;
   for (uint32_t i = b; i < e; i++) {
     uint32_t v = in[i];
-    acc += TASKS ? (v + kTaskLen - 1) / kTaskLen : v;
+    acc += TASKS ? (v + tl - 1) / tl : v;
   }
   sums[threadIdx.x] = acc;
   __syncthreads();
@@ -123,7 +219,7 @@ msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uin
   for (uint32_t i = b; i < e; i++) {
     out[i] = run;
     uint32_t v = in[i];
-    run += TASKS ? (v + kTaskLen - 1) / kTaskLen : v;
+    run += TASKS ? (v + tl - 1) / tl : v;
   }
   if (threadIdx.x == 1023) {
     out[n] = sums[1023];
@@ -131,45 +227,86 @@ msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uin
   }
 }
 
+// Bucket totals from the scanned sub-counters: bcount[b] = offsets[(b+1)*kCopies] - offsets[b*kCopies].
 __global__ void __launch_bounds__(256)
-msm_task_fill_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                     const uint32_t* __restrict__ task_off, uint2* __restrict__ tasks, uint32_t total_buckets) {
+msm_bucket_count_kernel(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ bcount, uint32_t n_buckets) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= total_buckets) return;
-  uint32_t cnt = counts[b], off = offsets[b], t = task_off[b];
-  for (uint32_t done = 0; done < cnt; done += kTaskLen, t++) {
-    uint32_t len = cnt - done < (uint32_t)kTaskLen ? cnt - done : (uint32_t)kTaskLen;
-    tasks[t] = make_uint2(off + done, len);
-  }
+  if (b >= n_buckets) return;
+  bcount[b] = offsets[(b + 1) * kCopies] - offsets[b * kCopies];
 }
 
+// One thread per task: find its bucket by binary search in task_off, then (first entry, length).
+__global__ void __launch_bounds__(256)
+msm_task_fill_kernel(const uint32_t* __restrict__ bcount, const uint32_t* __restrict__ offsets,
+                     const uint32_t* __restrict__ task_off, uint2* __restrict__ tasks, uint32_t n_buckets,
+                     const uint32_t* __restrict__ flags) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= flags[2]) return;
+  const uint32_t tl = flags[4];
+  uint32_t lo = 0, hi = n_buckets;  // task_off[lo] <= t < task_off[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (task_off[mid] <= t) lo = mid; else hi = mid;
+  }
+  const uint32_t done = (t - task_off[lo]) * tl;
+  const uint32_t left = bcount[lo] - done;
+  tasks[t] = make_uint2(offsets[lo * kCopies] + done, left < tl ? left : tl);
+}
+
+// ------------------------------------------------------------------------------------------------ run
+template <class T>
+__device__ __forceinline__ void prefetch_l1(const T* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  if (sizeof(T) > 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(p) + 64));
+}
+
+template <class F> struct AccumOcc { static constexpr int kBlocks = 5; };   // G1: <= 102 registers
+template <> struct AccumOcc<Fq2> { static constexpr int kBlocks = NZCP_G2_ACC_BLOCKS; };
+
 template <class F>
-__global__ void __launch_bounds__(128)
-msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(128, AccumOcc<F>::kBlocks)
+msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,
                       const uint2* __restrict__ tasks, const uint32_t* __restrict__ flags, XYZZ<F>* __restrict__ partial) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= flags[2]) return;
   uint2 tk = tasks[t];
   XYZZ<F> acc = XYZZ<F>::inf();
+  uint32_t e = entries[tk.x];
+  prefetch_l1(table + (e & 0x7fffffffu));
   for (uint32_t k = 0; k < tk.y; k++) {
-    uint32_t e = entries[tk.x + k];
-    Affine<F> q = bases[e & 0x7fffffffu];
-    if (q.is_inf()) continue;
-    xyzz_madd(acc, q, (e >> 31) != 0);
+    uint32_t en = e;
+    if (k + 1 < tk.y) {
+      en = entries[tk.x + k + 1];
+      prefetch_l1(table + (en & 0x7fffffffu));
+    }
+    Affine<F> q = table[e & 0x7fffffffu];
+    if (!q.is_inf()) xyzz_madd(acc, q, (e >> 31) != 0);
+    e = en;
   }
   partial[t] = acc;
 }
 
+template <class T>
+__device__ __forceinline__ T shfl_down_obj(const T& v, unsigned delta) {
+  T r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 4); i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+  return r;
+}
+
+// One thread per bucket sums the bucket's (few) task partials; buckets with many tasks go to the block-wide kernel.
 template <class F>
 __global__ void __launch_bounds__(128)
 msm_combine_kernel(const uint32_t* __restrict__ task_off, const XYZZ<F>* __restrict__ partial,
-                   XYZZ<F>* __restrict__ buckets, uint32_t total_buckets, uint32_t* __restrict__ heavy_list,
-                   uint32_t* __restrict__ flags) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= total_buckets) return;
-  uint32_t t0 = task_off[b], nt = task_off[b + 1] - t0;
-  if (nt > (uint32_t)kLightTasks) {
-    heavy_list[atomicAdd(&flags[0], 1u)] = b;
+                   XYZZ<F>* __restrict__ buckets, uint32_t n_buckets, uint32_t* __restrict__ heavy_list,
+                   uint32_t* __restrict__ heavy_count) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_buckets) return;
+  const uint32_t t0 = task_off[b], nt = task_off[b + 1] - t0;
+  if (nt > (uint32_t)kHeavyTasks) {
+    heavy_list[atomicAdd(heavy_count, 1u)] = b;
     return;
   }
   XYZZ<F> acc = XYZZ<F>::inf();
@@ -177,58 +314,124 @@ msm_combine_kernel(const uint32_t* __restrict__ task_off, const XYZZ<F>* __restr
   buckets[b] = acc;
 }
 
+// Heavy buckets (more than kHeavyTasks task partials; the witness's bucket "1" has ~15 000) are summed in two stages
+// so that no single block walks a long dependent chain: stage 1 reduces chunks of kHeavyChunk partials (one block per
+// chunk, all chunks of all heavy buckets in one grid), stage 2 sums each bucket's chunk results.
+__global__ void __launch_bounds__(256)
+msm_heavy_prepare_kernel(const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ heavy_list,
+                         const uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ chunk_cnt, uint32_t n_buckets) {
+  uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_buckets) return;
+  uint32_t v = 0;
+  if (h < *heavy_count) {
+    uint32_t b = heavy_list[h];
+    v = (task_off[b + 1] - task_off[b] + kHeavyChunk - 1) / kHeavyChunk;
+  }
+  chunk_cnt[h] = v;
+}
+
+template <class F>
+__device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F> acc, XYZZ<F>* sm) {
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t stride = kHeavyThreads / 2; stride >= 1; stride >>= 1) {
+    if (threadIdx.x < stride) {
+      XYZZ<F> a = sm[threadIdx.x];
+      xyzz_add(a, sm[threadIdx.x + stride]);
+      sm[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  XYZZ<F> r = sm[0];
+  __syncthreads();
+  return r;
+}
+
 template <class F>
 __global__ void __launch_bounds__(kHeavyThreads)
 msm_combine_heavy_kernel(const uint32_t* __restrict__ task_off, const XYZZ<F>* __restrict__ partial,
-                         XYZZ<F>* __restrict__ buckets, const uint32_t* __restrict__ heavy_list,
-                         const uint32_t* __restrict__ flags) {
+                         const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
+                         const uint32_t* __restrict__ chunk_off, XYZZ<F>* __restrict__ chunk_partial) {
   extern __shared__ unsigned char heavy_sm_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_sm_raw);
-  uint32_t n_heavy = flags[0];
-  for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
-    uint32_t b = heavy_list[h];
-    uint32_t t0 = task_off[b], nt = task_off[b + 1] - t0;
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t j = threadIdx.x; j < nt; j += blockDim.x) xyzz_add(acc, partial[t0 + j]);
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t stride = kHeavyThreads / 2; stride >= 1; stride >>= 1) {
-      if (threadIdx.x < stride) {
-        XYZZ<F> a = sm[threadIdx.x];
-        xyzz_add(a, sm[threadIdx.x + stride]);
-        sm[threadIdx.x] = a;
-      }
-      __syncthreads();
+  const uint32_t n_heavy = *heavy_count;
+  const uint32_t total = chunk_off[n_heavy];
+  for (uint32_t ch = blockIdx.x; ch < total; ch += gridDim.x) {
+    // heavy bucket h with chunk_off[h] <= ch < chunk_off[h + 1]
+    uint32_t lo = 0, hi = n_heavy;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (chunk_off[mid] <= ch) lo = mid; else hi = mid;
     }
-    if (threadIdx.x == 0) buckets[b] = sm[0];
-    __syncthreads();
+    const uint32_t b = heavy_list[lo];
+    const uint32_t c = ch - chunk_off[lo];
+    const uint32_t t0 = task_off[b] + c * kHeavyChunk;
+    const uint32_t left = task_off[b + 1] - t0;
+    const uint32_t cnt = left < (uint32_t)kHeavyChunk ? left : (uint32_t)kHeavyChunk;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) xyzz_add(acc, partial[t0 + j]);
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) chunk_partial[ch] = acc;
   }
 }
 
-// One level of the bucket-reduction tree.  Input "buckets" P[0..G) of a group carry weights 0..G-1:
-//   A = sum_j P[j],   S = sum_j j * P[j]   (running sums from the top),
-//   R = sum_j Rin[j] + 2^shift * S         (Rin = weighted sums of the children's own subtrees; absent at level 1)
-// so that at the top  sum_v v * B_v = R_top + A_top  (bucket id v-1 carries weight v-1, plus one A_top).
+template <class F>
+__global__ void __launch_bounds__(kHeavyThreads)
+msm_combine_heavy2_kernel(const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
+                          const uint32_t* __restrict__ chunk_off, const XYZZ<F>* __restrict__ chunk_partial,
+                          XYZZ<F>* __restrict__ buckets) {
+  extern __shared__ unsigned char heavy_sm_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_sm_raw);
+  const uint32_t n_heavy = *heavy_count;
+  for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    const uint32_t c0 = chunk_off[h], nc = chunk_off[h + 1] - c0;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t j = threadIdx.x; j < nc; j += blockDim.x) xyzz_add(acc, chunk_partial[c0 + j]);
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) buckets[heavy_list[h]] = acc;
+  }
+}
+
+// One level of the bucket-reduction tree, one warp per group of G = 2^g_log inputs carrying weights 0..G-1:
+//   A = sum_j P[j]                       (lane 0 of a suffix scan:  run_j = sum_{k>=j} P[k])
+//   S = sum_j j * P[j] = sum_{j>=1} run_j (tree sum over lanes)
+//   R = sum_j Rin[j] + 2^shift * S       (Rin = weighted sums of the children's own subtrees; absent at level 1)
+// At the top  sum_v v * B_v = R_top + A_top  (bucket id v-1 carries weight v-1, plus one A_top).
 template <class F>
 __global__ void __launch_bounds__(128)
 msm_reduce_level_kernel(const XYZZ<F>* __restrict__ in_a, const XYZZ<F>* __restrict__ in_r, XYZZ<F>* __restrict__ out_a,
                         XYZZ<F>* __restrict__ out_r, uint32_t n_groups, int g_log, int shift) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= n_groups) return;
   const uint32_t G = 1u << g_log;
   const size_t base = (size_t)g << g_log;
-  XYZZ<F> run = XYZZ<F>::inf(), S = XYZZ<F>::inf();
-  for (uint32_t j = G - 1; j >= 1; j--) {
-    xyzz_add(run, in_a[base + j]);
-    xyzz_add(S, run);
+  XYZZ<F> run = lane < G ? in_a[base + lane] : XYZZ<F>::inf();
+  for (uint32_t d = 1; d < G; d <<= 1) {
+    XYZZ<F> o = shfl_down_obj(run, d);
+    if (lane + d < G) xyzz_add(run, o);
   }
-  xyzz_add(run, in_a[base]);
-  for (int k = 0; k < shift; k++) S = xyzz_dbl(S);
+  XYZZ<F> leaf = (lane >= 1 && lane < G) ? run : XYZZ<F>::inf();
+  for (uint32_t off = 16; off >= 1; off >>= 1) {
+    if (off < G) {
+      XYZZ<F> o = shfl_down_obj(leaf, off);
+      xyzz_add(leaf, o);
+    }
+  }
+  for (int k = 0; k < shift; k++) leaf = xyzz_dbl(leaf);
   if (in_r) {
-    for (uint32_t j = 0; j < G; j++) xyzz_add(S, in_r[base + j]);
+    XYZZ<F> r = lane < G ? in_r[base + lane] : XYZZ<F>::inf();
+    for (uint32_t off = 16; off >= 1; off >>= 1) {
+      if (off < G) {
+        XYZZ<F> o = shfl_down_obj(r, off);
+        xyzz_add(r, o);
+      }
+    }
+    xyzz_add(leaf, r);
   }
-  out_a[g] = run;
-  out_r[g] = S;
+  if (lane == 0) {
+    out_a[g] = run;
+    out_r[g] = leaf;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -244,6 +447,12 @@ int msm_pick_window(size_t n) {
   return 16;
 }
 
+int msm_num_windows(int c) {
+  int w = (254 + c - 1) / c;
+  if (w * c < 255) w++;  // one spare bit so the top signed digit never carries out
+  return w;
+}
+
 template <class T>
 static T* dev_alloc(size_t count, size_t* total) {
   T* p = nullptr;
@@ -253,153 +462,247 @@ static T* dev_alloc(size_t count, size_t* total) {
   return p;
 }
 
-void msm_plan_create(MsmPlan* p, size_t n_points, bool g2, int c_override) {
-  *p = MsmPlan();
-  p->n_points = n_points;
-  p->g2 = g2;
-  p->c = c_override > 0 ? c_override : msm_pick_window(n_points ? n_points : 1);
-  if (p->c < 2 || p->c > 20) throw std::runtime_error("msm: window size out of range");
-  p->n_windows = (254 + p->c - 1) / p->c;
-  if (p->n_windows * p->c < 255) p->n_windows++;
-  p->n_buckets = (size_t)1 << (p->c - 1);
-  size_t tb = p->n_buckets * p->n_windows;
-  size_t max_entries = (size_t)p->n_windows * n_points;
-  if (max_entries >= ((size_t)1 << 32) || n_points >= ((size_t)1 << 31)) throw std::runtime_error("msm: too many points");
-  p->max_tasks = tb + max_entries / kTaskLen + 1;
-  size_t psz = g2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
-  size_t tot = 0;
-  p->counts = dev_alloc<uint32_t>(tb + 1, &tot);
-  p->offsets = dev_alloc<uint32_t>(tb + 1, &tot);
-  p->cursors = dev_alloc<uint32_t>(tb + 1, &tot);
-  p->entries = dev_alloc<uint32_t>(max_entries, &tot);
-  p->task_off = dev_alloc<uint32_t>(tb + 1, &tot);
-  p->tasks = dev_alloc<uint2>(p->max_tasks, &tot);
-  p->partial = dev_alloc<unsigned char>(p->max_tasks * psz, &tot);
-  p->buckets = dev_alloc<unsigned char>(tb * psz, &tot);
-  size_t lvl = (tb >> kGroupLog) + p->n_windows;
-  for (int i = 0; i < 2; i++) {
-    p->lvl_a[i] = dev_alloc<unsigned char>(lvl * psz, &tot);
-    p->lvl_r[i] = dev_alloc<unsigned char>(lvl * psz, &tot);
-  }
-  p->heavy_list = dev_alloc<uint32_t>(tb, &tot);
-  p->flags = dev_alloc<uint32_t>(8, &tot);
-  p->window_out = dev_alloc<unsigned char>(2 * p->n_windows * psz, &tot);
-  NZCP_CUDA(cudaMallocHost(&p->window_host, 2 * p->n_windows * psz + 64));
-  p->scratch_bytes = tot;
+void msm_table_create(MsmTable* t, const void* d_bases, size_t n_src, size_t pad_front, bool g2, int c, cudaStream_t st) {
+  *t = MsmTable();
+  if (c < 2 || c > 20) throw std::runtime_error("msm: window size out of range");
+  t->n_points = n_src + pad_front;
+  t->c = c;
+  t->n_windows = msm_num_windows(c);
+  t->g2 = g2;
+  size_t psz = g2 ? sizeof(G2Affine) : sizeof(G1Affine);
+  if ((size_t)t->n_windows * t->n_points >= ((size_t)1 << 31)) throw std::runtime_error("msm: too many points");
+  t->bytes = (size_t)t->n_windows * (t->n_points ? t->n_points : 1) * psz;
+  NZCP_CUDA(cudaMalloc(&t->pts, t->bytes));
+  if (t->n_points == 0) return;
+  unsigned grid = div_up(t->n_points, 128);
+  if (g2)
+    msm_table_kernel<Fq2><<<grid, 128, 0, st>>>(reinterpret_cast<const G2Affine*>(d_bases), n_src, pad_front,
+                                               reinterpret_cast<G2Affine*>(t->pts), t->n_points, c, t->n_windows);
+  else
+    msm_table_kernel<Fq><<<grid, 128, 0, st>>>(reinterpret_cast<const G1Affine*>(d_bases), n_src, pad_front,
+                                              reinterpret_cast<G1Affine*>(t->pts), t->n_points, c, t->n_windows);
+  NZCP_LAUNCH_CHECK();
 }
 
-void msm_plan_destroy(MsmPlan* p) {
-  cudaFree(p->counts);
-  cudaFree(p->offsets);
-  cudaFree(p->cursors);
-  cudaFree(p->entries);
-  cudaFree(p->task_off);
-  cudaFree(p->tasks);
-  cudaFree(p->partial);
-  cudaFree(p->buckets);
-  for (int i = 0; i < 2; i++) {
-    cudaFree(p->lvl_a[i]);
-    cudaFree(p->lvl_r[i]);
+void msm_table_destroy(MsmTable* t) {
+  cudaFree(t->pts);
+  *t = MsmTable();
+}
+
+void msm_sort_create(MsmSort* s, size_t n_points, int c) {
+  *s = MsmSort();
+  if (c < 2 || c > 20) throw std::runtime_error("msm: window size out of range");
+  s->n_points = n_points;
+  s->c = c;
+  s->n_windows = msm_num_windows(c);
+  s->n_buckets = (size_t)1 << (c - 1);
+  size_t max_entries = (size_t)s->n_windows * n_points;
+  if (max_entries >= ((size_t)1 << 31)) throw std::runtime_error("msm: too many points");
+  // task length L = clamp(pow2_floor(entries / kTargetTasks), 8, 64)  =>  tasks <= n_buckets + max(2 * target, entries / 64)
+  size_t by_len = max_entries / kTaskLenMax, by_target = 2 * (size_t)kTargetTasks;
+  if (max_entries / kTaskLenMin < by_target) by_target = max_entries / kTaskLenMin;
+  s->max_tasks = s->n_buckets + (by_len > by_target ? by_len : by_target) + 1;
+  size_t tot = 0;
+  size_t n_ctr = s->n_buckets * kCopies;
+  s->counts = dev_alloc<uint32_t>(n_ctr + 1, &tot);
+  s->offsets = dev_alloc<uint32_t>(n_ctr + 1, &tot);
+  s->cursors = dev_alloc<uint32_t>(n_ctr + 1, &tot);
+  s->bcount = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
+  s->block_sums = dev_alloc<uint32_t>(2 * (n_ctr / kScanBlock + 2), &tot);
+  s->entries = dev_alloc<uint32_t>(max_entries, &tot);
+  s->task_off = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
+  s->tasks = dev_alloc<uint2>(s->max_tasks, &tot);
+  s->flags = dev_alloc<uint32_t>(8, &tot);
+  NZCP_CUDA(cudaMallocHost(&s->flags_host, 8 * sizeof(uint32_t)));
+  memset(s->flags_host, 0, 8 * sizeof(uint32_t));
+  s->scratch_bytes = tot;
+}
+
+void msm_sort_destroy(MsmSort* s) {
+  cudaFree(s->counts);
+  cudaFree(s->offsets);
+  cudaFree(s->cursors);
+  cudaFree(s->bcount);
+  cudaFree(s->block_sums);
+  cudaFree(s->entries);
+  cudaFree(s->task_off);
+  cudaFree(s->tasks);
+  cudaFree(s->flags);
+  if (s->flags_host) cudaFreeHost(s->flags_host);
+  *s = MsmSort();
+}
+
+void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_t st) {
+  if (n_points > s->n_points) throw std::runtime_error("msm: sort plan too small");
+  const uint32_t nb = (uint32_t)s->n_buckets;
+  const uint32_t n_ctr = nb * kCopies;
+  NZCP_CUDA(cudaMemsetAsync(s->counts, 0, (n_ctr + 1) * sizeof(uint32_t), st));
+  NZCP_CUDA(cudaMemsetAsync(s->flags, 0, 8 * sizeof(uint32_t), st));
+  if (n_points) {
+    // entries index the table of the plan's full point count, so a shorter scalar vector still addresses T[w][i]
+    DigitParams dp{(uint32_t)n_points, (uint32_t)s->n_points, s->c, s->n_windows, nb};
+    unsigned gp = div_up(n_points, 256);
+    msm_digits_kernel<false><<<gp, 256, 0, st>>>(scalars, dp, s->counts, nullptr, s->flags);
+    NZCP_LAUNCH_CHECK();
+    // exclusive scan of the sub-counters (counts[n_ctr] = 0 is scanned too, so offsets[n_ctr] = total)
+    const uint32_t n_scan = n_ctr + 1;
+    const uint32_t n_blk = div_up(n_scan, kScanBlock);
+    uint32_t* blk_sum = s->block_sums;
+    uint32_t* blk_off = s->block_sums + (n_ctr / kScanBlock + 2);
+    msm_scan_sums_kernel<<<n_blk, 256, 0, st>>>(s->counts, blk_sum, n_scan);
+    NZCP_LAUNCH_CHECK();
+    msm_scan_kernel<false><<<1, 1024, 0, st>>>(blk_sum, blk_off, n_blk, s->flags + 3, s->flags);
+    NZCP_LAUNCH_CHECK();
+    msm_scan_apply_kernel<<<n_blk, 256, 0, st>>>(s->counts, blk_off, s->offsets, s->cursors, n_scan);
+    NZCP_LAUNCH_CHECK();
+    msm_digits_kernel<true><<<gp, 256, 0, st>>>(scalars, dp, s->cursors, s->entries, s->flags);
+    NZCP_LAUNCH_CHECK();
+    msm_bucket_count_kernel<<<div_up(nb, 256), 256, 0, st>>>(s->offsets, s->bcount, nb);
+    NZCP_LAUNCH_CHECK();
+    msm_scan_kernel<true><<<1, 1024, 0, st>>>(s->bcount, s->task_off, nb, s->flags + 2, s->flags);
+    NZCP_LAUNCH_CHECK();
+    msm_task_fill_kernel<<<div_up(s->max_tasks, 256), 256, 0, st>>>(s->bcount, s->offsets, s->task_off, s->tasks, nb, s->flags);
+    NZCP_LAUNCH_CHECK();
+  } else {
+    NZCP_CUDA(cudaMemsetAsync(s->task_off, 0, (nb + 1) * sizeof(uint32_t), st));
   }
-  cudaFree(p->heavy_list);
-  cudaFree(p->flags);
-  cudaFree(p->window_out);
-  if (p->window_host) cudaFreeHost(p->window_host);
-  *p = MsmPlan();
+  NZCP_CUDA(cudaMemcpyAsync(s->flags_host, s->flags, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+}
+
+uint32_t msm_sort_check(const MsmSort* s) {
+  if (s->flags_host[1]) throw std::runtime_error("witness/scalar value is not a canonical field element (>= r)");
+  return s->flags_host[3];
+}
+
+void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
+  *r = MsmRun();
+  r->g2 = g2;
+  size_t psz = g2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
+  size_t tot = 0;
+  r->partial = dev_alloc<unsigned char>(sort->max_tasks * psz, &tot);
+  r->buckets = dev_alloc<unsigned char>(sort->n_buckets * psz, &tot);
+  size_t lvl = (sort->n_buckets >> 1) + 1;
+  for (int i = 0; i < 2; i++) {
+    r->lvl_a[i] = dev_alloc<unsigned char>(lvl * psz, &tot);
+    r->lvl_r[i] = dev_alloc<unsigned char>(lvl * psz, &tot);
+  }
+  r->heavy_list = dev_alloc<uint32_t>(sort->n_buckets, &tot);
+  r->heavy_count = dev_alloc<uint32_t>(2, &tot);
+  r->chunk_cnt = dev_alloc<uint32_t>(sort->n_buckets + 1, &tot);
+  r->chunk_off = dev_alloc<uint32_t>(sort->n_buckets + 1, &tot);
+  r->chunk_partial = dev_alloc<unsigned char>((sort->max_tasks / kHeavyChunk + sort->n_buckets + 1) * psz, &tot);
+  r->out = dev_alloc<unsigned char>(2 * psz, &tot);
+  NZCP_CUDA(cudaMallocHost(&r->out_host, 2 * psz));
+  memset(r->out_host, 0, 2 * psz);
+  NZCP_CUDA(cudaEventCreate(&r->ev_acc0));
+  NZCP_CUDA(cudaEventCreate(&r->ev_acc1));
+  r->scratch_bytes = tot;
+}
+
+void msm_run_destroy(MsmRun* r) {
+  cudaFree(r->partial);
+  cudaFree(r->buckets);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(r->lvl_a[i]);
+    cudaFree(r->lvl_r[i]);
+  }
+  cudaFree(r->heavy_list);
+  cudaFree(r->heavy_count);
+  cudaFree(r->chunk_cnt);
+  cudaFree(r->chunk_off);
+  cudaFree(r->chunk_partial);
+  cudaFree(r->out);
+  if (r->out_host) cudaFreeHost(r->out_host);
+  if (r->ev_acc0) cudaEventDestroy(r->ev_acc0);
+  if (r->ev_acc1) cudaEventDestroy(r->ev_acc1);
+  *r = MsmRun();
 }
 
 template <class F>
-static void msm_launch_t(MsmPlan* p, const Affine<F>* bases, const Fr* scalars, size_t n_points, cudaStream_t st) {
-  if (n_points > p->n_points) throw std::runtime_error("msm: plan too small");
-  const size_t tb = p->n_buckets * p->n_windows;
+static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cudaStream_t st) {
+  if (t->c != s->c || t->n_points != s->n_points) throw std::runtime_error("msm: table and sort plan do not match");
+  const uint32_t nb = (uint32_t)s->n_buckets;
   const size_t psz = sizeof(XYZZ<F>);
-  uint32_t* host_flags = reinterpret_cast<uint32_t*>((unsigned char*)p->window_host + 2 * p->n_windows * psz);
-  NZCP_CUDA(cudaMemsetAsync(p->counts, 0, (tb + 1) * sizeof(uint32_t), st));
-  NZCP_CUDA(cudaMemsetAsync(p->flags, 0, 8 * sizeof(uint32_t), st));
-  XYZZ<F>* wout = reinterpret_cast<XYZZ<F>*>(p->window_out);
-  if (n_points == 0) {
-    NZCP_CUDA(cudaMemsetAsync(p->window_out, 0, 2 * p->n_windows * psz, st));
-  } else {
-    DigitParams dp{(uint32_t)n_points, p->c, p->n_windows, (uint32_t)p->n_buckets};
-    unsigned gp = div_up(n_points, 256);
-    msm_digits_kernel<false><<<gp, 256, 0, st>>>(scalars, dp, p->counts, nullptr, p->flags);
+  XYZZ<F>* partial = reinterpret_cast<XYZZ<F>*>(r->partial);
+  XYZZ<F>* buckets = reinterpret_cast<XYZZ<F>*>(r->buckets);
+  XYZZ<F>* out = reinterpret_cast<XYZZ<F>*>(r->out);
+  NZCP_CUDA(cudaMemsetAsync(r->heavy_count, 0, 2 * sizeof(uint32_t), st));
+  NZCP_CUDA(cudaEventRecord(r->ev_acc0, st));
+  msm_accumulate_kernel<F><<<div_up(s->max_tasks, 128), 128, 0, st>>>(reinterpret_cast<const Affine<F>*>(t->pts),
+                                                                     s->entries, s->tasks, s->flags, partial);
+  NZCP_LAUNCH_CHECK();
+  NZCP_CUDA(cudaEventRecord(r->ev_acc1, st));
+  msm_combine_kernel<F><<<div_up(nb, 128), 128, 0, st>>>(s->task_off, partial, buckets, nb, r->heavy_list,
+                                                                     r->heavy_count);
+  NZCP_LAUNCH_CHECK();
+  msm_heavy_prepare_kernel<<<div_up(nb, 256), 256, 0, st>>>(s->task_off, r->heavy_list, r->heavy_count, r->chunk_cnt, nb);
+  NZCP_LAUNCH_CHECK();
+  msm_scan_kernel<false><<<1, 1024, 0, st>>>(r->chunk_cnt, r->chunk_off, nb, r->heavy_count + 1, nullptr);
+  NZCP_LAUNCH_CHECK();
+  XYZZ<F>* chunk_partial = reinterpret_cast<XYZZ<F>*>(r->chunk_partial);
+  msm_combine_heavy_kernel<F><<<296, kHeavyThreads, kHeavyThreads * psz, st>>>(s->task_off, partial, r->heavy_list,
+                                                                               r->heavy_count, r->chunk_off, chunk_partial);
+  NZCP_LAUNCH_CHECK();
+  msm_combine_heavy2_kernel<F><<<148, kHeavyThreads, kHeavyThreads * psz, st>>>(r->heavy_list, r->heavy_count, r->chunk_off,
+                                                                                chunk_partial, buckets);
+  NZCP_LAUNCH_CHECK();
+  int bits_left = s->c - 1, shift = 0, level = 0;
+  const XYZZ<F>* in_a = buckets;
+  const XYZZ<F>* in_r = nullptr;
+  size_t groups_in = nb;
+  while (bits_left > 0) {
+    int g_log = bits_left < kGroupLog ? bits_left : kGroupLog;
+    size_t n_groups = groups_in >> g_log;
+    bool last = (bits_left == g_log);
+    XYZZ<F>* out_a = last ? out : reinterpret_cast<XYZZ<F>*>(r->lvl_a[level & 1]);
+    XYZZ<F>* out_r = last ? out + 1 : reinterpret_cast<XYZZ<F>*>(r->lvl_r[level & 1]);
+    msm_reduce_level_kernel<F><<<div_up(n_groups * 32, 128), 128, 0, st>>>(in_a, in_r, out_a, out_r, (uint32_t)n_groups,
+                                                                          g_log, shift);
     NZCP_LAUNCH_CHECK();
-    msm_scan_kernel<false><<<1, 1024, 0, st>>>(p->counts, p->offsets, (uint32_t)tb, nullptr);
-    NZCP_LAUNCH_CHECK();
-    NZCP_CUDA(cudaMemcpyAsync(p->cursors, p->offsets, (tb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    msm_digits_kernel<true><<<gp, 256, 0, st>>>(scalars, dp, p->cursors, p->entries, p->flags);
-    NZCP_LAUNCH_CHECK();
-    msm_scan_kernel<true><<<1, 1024, 0, st>>>(p->counts, p->task_off, (uint32_t)tb, p->flags + 2);
-    NZCP_LAUNCH_CHECK();
-    msm_task_fill_kernel<<<div_up(tb, 256), 256, 0, st>>>(p->counts, p->offsets, p->task_off, p->tasks, (uint32_t)tb);
-    NZCP_LAUNCH_CHECK();
-    XYZZ<F>* partial = reinterpret_cast<XYZZ<F>*>(p->partial);
-    XYZZ<F>* buckets = reinterpret_cast<XYZZ<F>*>(p->buckets);
-    msm_accumulate_kernel<F><<<div_up(p->max_tasks, 128), 128, 0, st>>>(bases, p->entries, p->tasks, p->flags, partial);
-    NZCP_LAUNCH_CHECK();
-    msm_combine_kernel<F><<<div_up(tb, 128), 128, 0, st>>>(p->task_off, partial, buckets, (uint32_t)tb, p->heavy_list,
-                                                         p->flags);
-    NZCP_LAUNCH_CHECK();
-    msm_combine_heavy_kernel<F><<<296, kHeavyThreads, kHeavyThreads * psz, st>>>(p->task_off, partial, buckets,
-                                                                               p->heavy_list, p->flags);
-    NZCP_LAUNCH_CHECK();
-    // reduction tree over the c-1 bucket-index bits
-    int bits_left = p->c - 1, shift = 0, level = 0;
-    const XYZZ<F>* in_a = buckets;
-    const XYZZ<F>* in_r = nullptr;
-    size_t groups_in = tb;
-    while (bits_left > 0) {
-      int g_log = bits_left < kGroupLog ? bits_left : kGroupLog;
-      size_t n_groups = groups_in >> g_log;
-      bool last = (bits_left == g_log);
-      XYZZ<F>* out_a = last ? wout : reinterpret_cast<XYZZ<F>*>(p->lvl_a[level & 1]);
-      XYZZ<F>* out_r = last ? wout + p->n_windows : reinterpret_cast<XYZZ<F>*>(p->lvl_r[level & 1]);
-      msm_reduce_level_kernel<F><<<div_up(n_groups, 128), 128, 0, st>>>(in_a, in_r, out_a, out_r, (uint32_t)n_groups,
-                                                                       g_log, shift);
-      NZCP_LAUNCH_CHECK();
-      in_a = out_a;
-      in_r = out_r;
-      groups_in = n_groups;
-      shift += g_log;
-      bits_left -= g_log;
-      level++;
-    }
+    in_a = out_a;
+    in_r = out_r;
+    groups_in = n_groups;
+    shift += g_log;
+    bits_left -= g_log;
+    level++;
   }
-  NZCP_CUDA(cudaMemcpyAsync(p->window_host, p->window_out, 2 * p->n_windows * psz, cudaMemcpyDeviceToHost, st));
-  NZCP_CUDA(cudaMemcpyAsync(host_flags, p->flags, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  NZCP_CUDA(cudaMemcpyAsync(r->out_host, r->out, 2 * psz, cudaMemcpyDeviceToHost, st));
 }
 
-void msm_launch(MsmPlan* p, const void* bases, const Fr* scalars, size_t n_points, cudaStream_t st) {
+void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     NZCP_CUDA(cudaFuncSetAttribute(msm_combine_heavy_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kHeavyThreads * sizeof(G2XYZZ))));
+    NZCP_CUDA(cudaFuncSetAttribute(msm_combine_heavy2_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kHeavyThreads * sizeof(G2XYZZ))));
     attr_done = true;
   }
-  if (p->g2)
-    msm_launch_t<Fq2>(p, reinterpret_cast<const G2Affine*>(bases), scalars, n_points, st);
+  if (r->g2 != table->g2) throw std::runtime_error("msm: run and table group mismatch");
+  if (r->g2)
+    msm_run_launch_t<Fq2>(r, sort, table, st);
   else
-    msm_launch_t<Fq>(p, reinterpret_cast<const G1Affine*>(bases), scalars, n_points, st);
+    msm_run_launch_t<Fq>(r, sort, table, st);
 }
 
 template <class F>
-static XYZZ<F> msm_finish_t(const MsmPlan* p) {
-  const size_t psz = sizeof(XYZZ<F>);
-  const XYZZ<F>* w = reinterpret_cast<const XYZZ<F>*>(p->window_host);
-  const uint32_t* host_flags = reinterpret_cast<const uint32_t*>((const unsigned char*)p->window_host + 2 * p->n_windows * psz);
-  if (host_flags[1]) throw std::runtime_error("witness/scalar value is not a canonical field element (>= r)");
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (int i = p->n_windows - 1; i >= 0; i--) {
-    if (!acc.is_inf())
-      for (int k = 0; k < p->c; k++) acc = xyzz_dbl(acc);
-    XYZZ<F> t = w[i];
-    xyzz_add(t, w[p->n_windows + i]);
-    xyzz_add(acc, t);
-  }
+static XYZZ<F> msm_run_finish_t(const MsmRun* r) {
+  const XYZZ<F>* w = reinterpret_cast<const XYZZ<F>*>(r->out_host);
+  XYZZ<F> acc = w[0];
+  xyzz_add(acc, w[1]);
   return acc;
 }
 
-G1XYZZ msm_finish_g1(const MsmPlan* p) { return msm_finish_t<Fq>(p); }
-G2XYZZ msm_finish_g2(const MsmPlan* p) { return msm_finish_t<Fq2>(p); }
+G1XYZZ msm_run_finish_g1(const MsmRun* r) { return msm_run_finish_t<Fq>(r); }
+G2XYZZ msm_run_finish_g2(const MsmRun* r) { return msm_run_finish_t<Fq2>(r); }
+
+float msm_run_accumulate_ms(const MsmRun* r) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, r->ev_acc0, r->ev_acc1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return ms;
+}
 
 }  // namespace nzcp

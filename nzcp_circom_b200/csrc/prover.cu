@@ -69,8 +69,8 @@ struct nzcp_zkey {
   G1Affine alpha1, beta1, delta1;  // Montgomery affine, as stored
   G2Affine beta2, gamma2, delta2;
   R1csDevice r1cs;
-  G1Affine *d_A = nullptr, *d_B1 = nullptr, *d_C = nullptr, *d_H = nullptr;
-  G2Affine* d_B2 = nullptr;
+  int c_w = 0, c_h = 0;                          // MSM window bits for the witness MSMs / the H MSM
+  MsmTable tab_a, tab_b1, tab_b2, tab_c, tab_h;  // window tables of sections 5-9 (tab_c front-padded to n_vars)
   NttDomain dom;
   size_t device_bytes = 0;
 };
@@ -79,12 +79,13 @@ struct nzcp_prover {
   nzcp_zkey* zk = nullptr;
   cudaStream_t st_main = nullptr;
   cudaStream_t st_msm[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev[16];
+  cudaEvent_t ev[20];
   int n_ev = 0;
   Fr* d_wtns = nullptr;
   Fr* d_abc = nullptr;
   Fr* d_h = nullptr;
-  MsmPlan plan_a, plan_b1, plan_b2, plan_c, plan_h;
+  MsmSort sort_w, sort_h;                       // bucket sorts of the witness and of the h scalars
+  MsmRun run_a, run_b1, run_b2, run_c, run_h;
 };
 
 namespace nzcp {
@@ -95,11 +96,11 @@ static void zkey_release(nzcp_zkey* zk) {
   cudaFree(zk->r1cs.row_ptr);
   cudaFree(zk->r1cs.col);
   cudaFree(zk->r1cs.val);
-  cudaFree(zk->d_A);
-  cudaFree(zk->d_B1);
-  cudaFree(zk->d_B2);
-  cudaFree(zk->d_C);
-  cudaFree(zk->d_H);
+  msm_table_destroy(&zk->tab_a);
+  msm_table_destroy(&zk->tab_b1);
+  msm_table_destroy(&zk->tab_b2);
+  msm_table_destroy(&zk->tab_c);
+  msm_table_destroy(&zk->tab_h);
   ntt_domain_destroy(&zk->dom);
   delete zk;
 }
@@ -179,11 +180,27 @@ static nzcp_zkey* zkey_load_impl(const uint8_t* b, size_t len, int device) {
   zk->r1cs.row_ptr = upload<uint32_t>(row_ptr.data(), row_ptr.size() * 4, &tot);
   zk->r1cs.col = upload<uint32_t>(col.data(), nc * 4, &tot);
   zk->r1cs.val = upload<Fr>(val.data(), nc * 32, &tot);
-  zk->d_A = upload<G1Affine>(s[5].p, s[5].len, &tot);
-  zk->d_B1 = upload<G1Affine>(s[6].p, s[6].len, &tot);
-  zk->d_B2 = upload<G2Affine>(s[7].p, s[7].len, &tot);
-  zk->d_C = upload<G1Affine>(s[8].p, s[8].len, &tot);
-  zk->d_H = upload<G1Affine>(s[9].p, s[9].len, &tot);
+  // sections 5-9 -> window tables (one-time expansion; the raw section is only staged)
+  zk->c_w = msm_pick_window(m);
+  zk->c_h = msm_pick_window(n);
+  auto make_table = [&](MsmTable* t, const Section& sec, size_t count, size_t pad, bool g2, int c) {
+    size_t dummy = 0;
+    void* raw = upload<unsigned char>(sec.p, sec.len, &dummy);
+    try {
+      msm_table_create(t, raw, count, pad, g2, c, 0);
+      NZCP_CUDA(cudaDeviceSynchronize());
+    } catch (...) {
+      cudaFree(raw);
+      throw;
+    }
+    cudaFree(raw);
+    tot += t->bytes;
+  };
+  make_table(&zk->tab_a, s[5], m, 0, false, zk->c_w);
+  make_table(&zk->tab_b1, s[6], m, 0, false, zk->c_w);
+  make_table(&zk->tab_b2, s[7], m, 0, true, zk->c_w);
+  make_table(&zk->tab_c, s[8], m - zk->n_public - 1, zk->n_public + 1, false, zk->c_w);
+  make_table(&zk->tab_h, s[9], n, 0, false, zk->c_h);
   ntt_domain_create(&zk->dom, (int)zk->power, 0);
   tot += ((size_t)n / 2 * 2 + n) * sizeof(Fr);
   zk->device_bytes = tot;
@@ -200,11 +217,13 @@ static void prover_release(nzcp_prover* p) {
   cudaFree(p->d_wtns);
   cudaFree(p->d_abc);
   cudaFree(p->d_h);
-  msm_plan_destroy(&p->plan_a);
-  msm_plan_destroy(&p->plan_b1);
-  msm_plan_destroy(&p->plan_b2);
-  msm_plan_destroy(&p->plan_c);
-  msm_plan_destroy(&p->plan_h);
+  msm_run_destroy(&p->run_a);
+  msm_run_destroy(&p->run_b1);
+  msm_run_destroy(&p->run_b2);
+  msm_run_destroy(&p->run_c);
+  msm_run_destroy(&p->run_h);
+  msm_sort_destroy(&p->sort_w);
+  msm_sort_destroy(&p->sort_h);
   delete p;
 }
 
@@ -214,7 +233,7 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
   p->zk = zk;
   NZCP_CUDA(cudaStreamCreateWithFlags(&p->st_main, cudaStreamNonBlocking));
   for (int i = 0; i < 4; i++) NZCP_CUDA(cudaStreamCreateWithFlags(&p->st_msm[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 16; i++) {
+  for (int i = 0; i < 20; i++) {
     NZCP_CUDA(cudaEventCreate(&p->ev[i]));
     p->n_ev = i + 1;
   }
@@ -222,11 +241,13 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
   NZCP_CUDA(cudaMalloc(&p->d_wtns, (size_t)zk->n_vars * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_abc, 3 * n * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_h, n * sizeof(Fr)));
-  msm_plan_create(&p->plan_a, zk->n_vars, false, 0);
-  msm_plan_create(&p->plan_b1, zk->n_vars, false, 0);
-  msm_plan_create(&p->plan_b2, zk->n_vars, true, 0);
-  msm_plan_create(&p->plan_c, zk->n_vars - zk->n_public - 1, false, 0);
-  msm_plan_create(&p->plan_h, n, false, 0);
+  msm_sort_create(&p->sort_w, zk->n_vars, zk->c_w);
+  msm_sort_create(&p->sort_h, n, zk->c_h);
+  msm_run_create(&p->run_a, &p->sort_w, false);
+  msm_run_create(&p->run_b1, &p->sort_w, false);
+  msm_run_create(&p->run_b2, &p->sort_w, true);
+  msm_run_create(&p->run_c, &p->sort_w, false);
+  msm_run_create(&p->run_h, &p->sort_h, false);
   return p.release();
 }
 
@@ -244,7 +265,8 @@ static void random_fr(uint8_t out[32]) {
   fclose(f);
 }
 
-// Event slots: 0 start, 1 upload done, 2 eval done, 3 ntt+join done, 4 msm H done, 5..12 msm A,B1,B2,C (begin,end)
+// Event slots: 0 start, 1 upload done, 2 eval done, 3 ntt+join done, 4 msm H done, 5 witness sort done,
+// 6..13 msm A,B1,B2,C (begin,end), 14 h sort done
 static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_witness_ext, const uint8_t* r_in,
                        const uint8_t* s_in, nzcp_proof* proof, nzcp_prove_debug* dbg) {
   nzcp_zkey* zk = p->zk;
@@ -254,7 +276,7 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
   if (s_in) memcpy(sb, s_in, 32); else random_fr(sb);
   if (!fr_bytes_canonical(rb) || !fr_bytes_canonical(sb)) throw ApiError(NZCP_E_ARG, "blinding scalar r or s is not < r");
   use_device(zk->device);
-  const size_t n = zk->domain_size, m = zk->n_vars, npub = zk->n_public;
+  const size_t n = zk->domain_size, m = zk->n_vars;
   cudaStream_t sm = p->st_main;
   NZCP_CUDA(cudaEventRecord(p->ev[0], sm));
   const Fr* d_w = d_witness_ext;
@@ -263,17 +285,21 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
     d_w = p->d_wtns;
   }
   NZCP_CUDA(cudaEventRecord(p->ev[1], sm));
-  // witness MSMs on their own streams (snarkjs order: A, B1, B2, C)
-  struct Job { MsmPlan* plan; const void* bases; const Fr* sc; size_t cnt; };
-  Job jobs[4] = {{&p->plan_a, zk->d_A, d_w, m},
-                 {&p->plan_b1, zk->d_B1, d_w, m},
-                 {&p->plan_b2, zk->d_B2, d_w, m},
-                 {&p->plan_c, zk->d_C, d_w + npub + 1, m - npub - 1}};
+  // The four witness MSMs (snarkjs order: A, B1, B2, C) share ONE bucket sort of the witness; the C table is
+  // front-padded with nPublic+1 infinity points so it is indexed by wire number like the others.
+  // B2 (G2, the longest) is sorted for on its own stream and launched first.
+  cudaStream_t sw = p->st_msm[2];
+  NZCP_CUDA(cudaStreamWaitEvent(sw, p->ev[1], 0));
+  msm_sort_launch(&p->sort_w, d_w, m, sw);
+  NZCP_CUDA(cudaEventRecord(p->ev[5], sw));
+  struct Job { MsmRun* run; const MsmTable* tab; int stream; };
+  Job jobs[4] = {{&p->run_b2, &zk->tab_b2, 2}, {&p->run_a, &zk->tab_a, 0}, {&p->run_b1, &zk->tab_b1, 1}, {&p->run_c, &zk->tab_c, 3}};
   for (int k = 0; k < 4; k++) {
-    NZCP_CUDA(cudaStreamWaitEvent(p->st_msm[k], p->ev[1], 0));
-    NZCP_CUDA(cudaEventRecord(p->ev[5 + 2 * k], p->st_msm[k]));
-    msm_launch(jobs[k].plan, jobs[k].bases, jobs[k].sc, jobs[k].cnt, p->st_msm[k]);
-    NZCP_CUDA(cudaEventRecord(p->ev[6 + 2 * k], p->st_msm[k]));
+    cudaStream_t st = p->st_msm[jobs[k].stream];
+    if (st != sw) NZCP_CUDA(cudaStreamWaitEvent(st, p->ev[5], 0));
+    NZCP_CUDA(cudaEventRecord(p->ev[6 + 2 * jobs[k].stream], st));
+    msm_run_launch(jobs[k].run, &p->sort_w, jobs[k].tab, st);
+    NZCP_CUDA(cudaEventRecord(p->ev[7 + 2 * jobs[k].stream], st));
   }
   // H pipeline on the main stream
   r1cs_eval(zk->r1cs, d_w, p->d_abc, sm);
@@ -281,7 +307,9 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
   ntt_coset_pipeline(zk->dom, p->d_abc, 3, sm);
   ntt_join_abc(p->d_abc, p->d_abc + n, p->d_abc + 2 * n, p->d_h, n, sm);
   NZCP_CUDA(cudaEventRecord(p->ev[3], sm));
-  msm_launch(&p->plan_h, zk->d_H, p->d_h, n, sm);
+  msm_sort_launch(&p->sort_h, p->d_h, n, sm);
+  NZCP_CUDA(cudaEventRecord(p->ev[14], sm));
+  msm_run_launch(&p->run_h, &p->sort_h, &zk->tab_h, sm);
   NZCP_CUDA(cudaEventRecord(p->ev[4], sm));
   if (dbg && dbg->h_scalars) NZCP_CUDA(cudaMemcpyAsync(dbg->h_scalars, p->d_h, n * sizeof(Fr), cudaMemcpyDeviceToHost, sm));
   for (int k = 0; k < 4; k++) NZCP_CUDA(cudaStreamSynchronize(p->st_msm[k]));
@@ -289,15 +317,18 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
 
   G1XYZZ A, B1, C, H;
   G2XYZZ B2;
+  uint32_t ent_w = 0, ent_h = 0;
   try {
-    A = msm_finish_g1(&p->plan_a);
-    B1 = msm_finish_g1(&p->plan_b1);
-    B2 = msm_finish_g2(&p->plan_b2);
-    C = msm_finish_g1(&p->plan_c);
-    H = msm_finish_g1(&p->plan_h);
+    ent_w = msm_sort_check(&p->sort_w);
+    ent_h = msm_sort_check(&p->sort_h);
   } catch (const std::runtime_error& e) {
     throw ApiError(NZCP_E_RANGE, e.what());
   }
+  A = msm_run_finish_g1(&p->run_a);
+  B1 = msm_run_finish_g1(&p->run_b1);
+  B2 = msm_run_finish_g2(&p->run_b2);
+  C = msm_run_finish_g1(&p->run_c);
+  H = msm_run_finish_g1(&p->run_h);
   if (dbg) {
     g1_to_plain_bytes(A, dbg->msm_a);
     g1_to_plain_bytes(B1, dbg->msm_b1);
@@ -309,11 +340,21 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
     dbg->stage_ms[0] = el(0, 1);
     dbg->stage_ms[1] = el(1, 2);
     dbg->stage_ms[2] = el(2, 3);
-    dbg->stage_ms[3] = el(5, 6);
-    dbg->stage_ms[4] = el(7, 8);
-    dbg->stage_ms[5] = el(9, 10);
-    dbg->stage_ms[6] = el(11, 12);
+    dbg->stage_ms[3] = el(6, 7);
+    dbg->stage_ms[4] = el(8, 9);
+    dbg->stage_ms[5] = el(10, 11);
+    dbg->stage_ms[6] = el(12, 13);
     dbg->stage_ms[7] = el(3, 4);
+    dbg->sort_ms[0] = el(1, 5);
+    dbg->sort_ms[1] = el(3, 14);
+    dbg->accumulate_ms[0] = msm_run_accumulate_ms(&p->run_a);
+    dbg->accumulate_ms[1] = msm_run_accumulate_ms(&p->run_b1);
+    dbg->accumulate_ms[2] = msm_run_accumulate_ms(&p->run_b2);
+    dbg->accumulate_ms[3] = msm_run_accumulate_ms(&p->run_c);
+    dbg->accumulate_ms[4] = msm_run_accumulate_ms(&p->run_h);
+    dbg->n_entries[0] = ent_w;
+    dbg->n_entries[1] = ent_h;
+    dbg->total_ms = el(0, 4);
   }
   // finalisation (tail of groth16Prove): O(1) group operations on the host, as snarkjs does on its main thread
   Fr r = fp_from_bytes_plain<FrParams>(rb), s = fp_from_bytes_plain<FrParams>(sb);

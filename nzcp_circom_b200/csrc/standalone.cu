@@ -154,10 +154,12 @@ static uint32_t selftest_curve(const Affine<F>& gen, uint64_t seed, uint32_t n) 
 
 // ------------------------------------------------------------------------------------------------ integer-pipe peak
 // Microbenchmarks behind the MSM / NTT roofline denominator (MEASURED_PEAKS.json has no integer-pipe figure):
-//   mode 0: independent mad.wide.u32 chains (IMAD.WIDE.U32), the instruction the Montgomery product is made of
+//   mode 0: mad.wide.u32 with loop-invariant multiplicands -- ptxas strength-reduces it to IADD3/IADD3.X pairs, so this
+//           measures the 64-bit add rate, NOT the multiplier (kept as a warning; the IMAD.WIDE rate is modes 3..5)
 //   mode 1: independent mad.lo.u32 chains (IMAD)
 //   mode 2: fp_mul<Fq> chains, 2 independent products per thread (what a kernel that did nothing else would reach)
-__global__ void __launch_bounds__(256) intpipe_kernel(int mode, int iters, uint32_t seed, uint32_t* sink) {
+template <int mode>
+__global__ void __launch_bounds__(256) intpipe_kernel(int iters, uint32_t seed, uint32_t* sink) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (mode == 0) {
     unsigned long long a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
@@ -189,6 +191,72 @@ __global__ void __launch_bounds__(256) intpipe_kernel(int mode, int iters, uint3
     }
     uint32_t s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
     if (s == 0x12345678u) sink[0] = s;
+  } else if (mode >= 3 && mode <= 8) {
+    // carry-chain variants: which form of IMAD.WIDE pays the half-rate penalty?
+    //   3: 2-long chains  mad.lo.cc / madc.hi           (IMAD.WIDE with no external carry)
+    //   4: 4-long chains  lo.cc hi.cc lo.cc hi          (1 carry-out + 1 carry-in)
+    //   5: 8-long chains                                (1 carry-out + 2 in/out + 1 carry-in)
+    //   6: mode 0 plus an independent add.cc/addc chain per IMAD (do the fma and alu pipes overlap?)
+    uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+    uint32_t c0 = t, c1 = t, c2 = t, c3 = t, c4 = t, c5 = t, c6 = t, c7 = t;
+    uint32_t x = seed | 1, y = seed + t;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (mode == 3) {
+          asm volatile("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.u32 %1, %8, %9, %1;\n\t"
+                       "mad.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.u32 %3, %8, %9, %3;\n\t"
+                       "mad.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.u32 %5, %8, %9, %5;\n\t"
+                       "mad.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+                       : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                       : "r"(x), "r"(y));
+        } else if (mode == 4) {
+          asm volatile("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+                       "madc.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.u32 %3, %8, %9, %3;\n\t"
+                       "mad.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.cc.u32 %5, %8, %9, %5;\n\t"
+                       "madc.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+                       : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                       : "r"(x), "r"(y));
+        } else if (mode == 5) {
+          asm volatile("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+                       "madc.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.cc.u32 %3, %8, %9, %3;\n\t"
+                       "madc.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.cc.u32 %5, %8, %9, %5;\n\t"
+                       "madc.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+                       : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                       : "r"(x), "r"(y));
+        } else if (mode == 7) {   // 8 add-with-carry instructions per step, no multiplies
+          asm volatile("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %8;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.u32 %3, %3, %8;\n\t"
+                       "add.cc.u32 %4, %4, %8;\n\taddc.cc.u32 %5, %5, %8;\n\taddc.cc.u32 %6, %6, %8;\n\taddc.u32 %7, %7, %8;"
+                       : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7)
+                       : "r"(y));
+        } else if (mode == 8) {   // 4 plain mad.wide + 8 add-with-carry
+          unsigned long long w0 = ((unsigned long long)a1 << 32) | a0, w1 = ((unsigned long long)a3 << 32) | a2;
+          unsigned long long w2 = ((unsigned long long)a5 << 32) | a4, w3 = ((unsigned long long)a7 << 32) | a6;
+          asm volatile("mad.wide.u32 %0, %4, %5, %0;\n\tmad.wide.u32 %1, %4, %5, %1;\n\t"
+                       "mad.wide.u32 %2, %4, %5, %2;\n\tmad.wide.u32 %3, %4, %5, %3;"
+                       : "+l"(w0), "+l"(w1), "+l"(w2), "+l"(w3) : "r"(c0), "r"(c4));
+          a0 = (uint32_t)w0; a1 = (uint32_t)(w0 >> 32); a2 = (uint32_t)w1; a3 = (uint32_t)(w1 >> 32);
+          a4 = (uint32_t)w2; a5 = (uint32_t)(w2 >> 32); a6 = (uint32_t)w3; a7 = (uint32_t)(w3 >> 32);
+          asm volatile("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %8;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.u32 %3, %3, %8;\n\t"
+                       "add.cc.u32 %4, %4, %8;\n\taddc.cc.u32 %5, %5, %8;\n\taddc.cc.u32 %6, %6, %8;\n\taddc.u32 %7, %7, %8;"
+                       : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7)
+                       : "r"(y));
+        } else {
+          asm volatile("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.u32 %1, %8, %9, %1;\n\t"
+                       "mad.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.u32 %3, %8, %9, %3;\n\t"
+                       "mad.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.u32 %5, %8, %9, %5;\n\t"
+                       "mad.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+                       : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                       : "r"(x), "r"(y));
+          asm volatile("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %8;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.u32 %3, %3, %8;\n\t"
+                       "add.cc.u32 %4, %4, %8;\n\taddc.cc.u32 %5, %5, %8;\n\taddc.cc.u32 %6, %6, %8;\n\taddc.u32 %7, %7, %8;"
+                       : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7)
+                       : "r"(y));
+        }
+      }
+    }
+    uint32_t sx = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    if (sx == 0x12345678u) sink[0] = sx;
   } else {
     Fq a = Fq::one(), b = Fq::r2(), c = Fq::one();
     a.v[0] ^= t & 0xffff;
@@ -207,7 +275,27 @@ using namespace nzcp;
 
 extern "C" {
 
-int nzcp_intpipe_bench(int device, int iters, double out[4]) {
+}  // extern "C"
+
+static void launch_intpipe(int mode, int blocks, int threads, int it, uint32_t seed, uint32_t* sink) {
+  switch (mode) {
+    case 0: intpipe_kernel<0><<<blocks, threads>>>(it, seed, sink); break;
+    case 1: intpipe_kernel<1><<<blocks, threads>>>(it, seed, sink); break;
+    case 2: intpipe_kernel<2><<<blocks, threads>>>(it, seed, sink); break;
+    case 3: intpipe_kernel<3><<<blocks, threads>>>(it, seed, sink); break;
+    case 4: intpipe_kernel<4><<<blocks, threads>>>(it, seed, sink); break;
+    case 5: intpipe_kernel<5><<<blocks, threads>>>(it, seed, sink); break;
+    case 6: intpipe_kernel<6><<<blocks, threads>>>(it, seed, sink); break;
+    case 7: intpipe_kernel<7><<<blocks, threads>>>(it, seed, sink); break;
+    default: intpipe_kernel<8><<<blocks, threads>>>(it, seed, sink); break;
+  }
+}
+
+extern "C" {
+
+// Per-mode raw rates for modes 0..8 -- diagnostic.  out[m] = per-second count of: mads (0, 1), Fq products (2),
+// 32x32 products (3..6), add-with-carry instructions (7), mad.wide (8: each accompanied by two add-with-carry).
+int nzcp_intpipe_modes(int device, int iters, double out[10]) {
   return api_guard([&] {
     if (!out || iters < 1) throw ApiError(NZCP_E_ARG, "bad argument");
     use_device(device);
@@ -215,21 +303,34 @@ int nzcp_intpipe_bench(int device, int iters, double out[4]) {
     NZCP_CUDA(cudaGetDeviceProperties(&prop, device));
     DevBuf sink(64);
     const int blocks = prop.multiProcessorCount * 8, threads = 256;
-    const double per_thread[3] = {64.0 * iters, 64.0 * iters, 2.0 * iters};
-    for (int mode = 0; mode < 3; mode++) {
+    for (int mode = 0; mode < 9; mode++) {
       int it = mode == 2 ? (iters / 16 > 0 ? iters / 16 : 1) : iters;
       float best = 1e30f;
       for (int rep = 0; rep < 4; rep++) {
         Timer t(0);
-        intpipe_kernel<<<blocks, threads>>>(mode, it, 12345u + rep, sink.as<uint32_t>());
+        launch_intpipe(mode, blocks, threads, it, 12345u + rep, sink.as<uint32_t>());
         NZCP_LAUNCH_CHECK();
         float ms = t.stop();
         if (rep && ms < best) best = ms;
       }
-      double ops = (mode == 2 ? 2.0 * it : per_thread[mode]) * (double)blocks * threads;
-      out[mode] = ops / (best * 1e-3);
+      // modes 0,1: 64 mads per iteration; modes 3..6: 64 mad.lo/hi halves = 32 wide products per iteration
+      double per_thread = mode == 2 ? 2.0 * it : (mode <= 1 || mode == 7 ? 64.0 * it : 32.0 * it);
+      out[mode] = per_thread * (double)blocks * threads / (best * 1e-3);
     }
-    out[3] = (double)prop.multiProcessorCount;
+    out[9] = (double)prop.multiProcessorCount;
+  });
+}
+
+int nzcp_intpipe_bench(int device, int iters, double out[4]) {
+  return api_guard([&] {
+    if (!out || iters < 1) throw ApiError(NZCP_E_ARG, "bad argument");
+    double m[10];
+    int rc = nzcp_intpipe_modes(device, iters, m);
+    if (rc != NZCP_OK) throw ApiError(rc, nzcp_last_error());
+    out[0] = m[3];  // IMAD.WIDE.U32 (independent 2-long carry chains; the .X forms run at the same rate)
+    out[1] = m[1];  // IMAD (32-bit)
+    out[2] = m[2];  // Fq Montgomery products, dependent chains
+    out[3] = m[9];
   });
 }
 
@@ -277,23 +378,36 @@ int nzcp_msm(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int 
     if (!out || (n_points && (!bases || !scalars))) throw ApiError(NZCP_E_ARG, "null argument");
     use_device(device);
     size_t bsz = g2 ? 128 : 64;
-    MsmPlan plan;
-    msm_plan_create(&plan, n_points, g2 != 0, window_bits);
-    struct Guard { MsmPlan* p; ~Guard() { msm_plan_destroy(p); } } gd{&plan};
+    int c = window_bits > 0 ? window_bits : msm_pick_window(n_points ? n_points : 1);
     DevBuf db(n_points * bsz), ds(n_points * 32);
     if (n_points) {
       NZCP_CUDA(cudaMemcpy(db.p, bases, n_points * bsz, cudaMemcpyHostToDevice));
       NZCP_CUDA(cudaMemcpy(ds.p, scalars, n_points * 32, cudaMemcpyHostToDevice));
     }
+    MsmTable tab;
+    MsmSort sort;
+    MsmRun run;
+    struct Guard {
+      MsmTable* t; MsmSort* s; MsmRun* r;
+      ~Guard() { msm_run_destroy(r); msm_sort_destroy(s); msm_table_destroy(t); }
+    } gd{&tab, &sort, &run};
+    // one-time per base set (the prover does this at zkey load); not part of kernel_ms
+    msm_table_create(&tab, db.p, n_points, 0, g2 != 0, c, 0);
+    msm_sort_create(&sort, n_points, c);
+    msm_run_create(&run, &sort, g2 != 0);
+    NZCP_CUDA(cudaDeviceSynchronize());
     Timer t(0);
-    msm_launch(&plan, db.p, ds.as<Fr>(), n_points, 0);
+    msm_sort_launch(&sort, ds.as<Fr>(), n_points, 0);
+    msm_run_launch(&run, &sort, &tab, 0);
     float ms = t.stop();
+    NZCP_CUDA(cudaDeviceSynchronize());
     if (kernel_ms) *kernel_ms = ms;
     try {
-      if (g2) g2_to_plain_bytes(msm_finish_g2(&plan), out); else g1_to_plain_bytes(msm_finish_g1(&plan), out);
+      msm_sort_check(&sort);
     } catch (const std::runtime_error& e) {
       throw ApiError(NZCP_E_RANGE, e.what());
     }
+    if (g2) g2_to_plain_bytes(msm_run_finish_g2(&run), out); else g1_to_plain_bytes(msm_run_finish_g1(&run), out);
   });
 }
 

@@ -29,7 +29,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Proof) == 256
     assert C.sizeof(_lib.ZkeyInfo) == 4 * 4 + 8 + 3 * 64 + 3 * 128 + 8
-    assert C.sizeof(_lib.ProveDebug) == 4 * 64 + 128 + 8 + 8 * 4
+    assert C.sizeof(_lib.ProveDebug) == 4 * 64 + 128 + 8 + (8 + 2 + 5 + 2 + 1) * 4
 
 
 @pytest.mark.parametrize("field,p", [(0, R), (1, Q)])
