@@ -133,6 +133,9 @@ int nzcp_host_root_of_unity(int k, uint8_t* out_plain);
 
 /* ---- synthetic circuits of the NZCP shape (no circom / snarkjs in this environment) ---- */
 typedef struct nzcp_synth nzcp_synth;
+/* n_points pseudo-random group elements k_i * G (Montgomery affine, 64 / 128 B each) into a host buffer -- bases for the
+ * standalone MSM sweeps.  Computed on `device` by the fixed-base kernel. */
+int nzcp_synth_points(uint64_t seed, size_t n_points, int g2, int device, uint8_t* out);
 /* Random forward-solvable R1CS: n_constraints constraints, n_public public outputs, n_free free inputs, each
  * constraint defines one fresh wire.  Wire value classes (bits / bytes / full-width) follow SURVEY.md 8d. */
 int nzcp_synth_create(uint64_t seed, uint32_t n_constraints, uint32_t n_public, uint32_t n_free, nzcp_synth** out);

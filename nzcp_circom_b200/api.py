@@ -282,6 +282,13 @@ def host_root_of_unity(k):
 
 
 # ------------------------------------------------------------------------------------------------ synthetic circuits
+def synth_points(seed, n_points, g2=False, device=0):
+    """n pseudo-random points k_i * G as a bytearray of Montgomery affine coordinates (zkey section format)."""
+    out = bytearray(n_points * (128 if g2 else 64))
+    check(_lib.load().nzcp_synth_points(int(seed), int(n_points), int(bool(g2)), int(device), addr(out) if n_points else None))
+    return out
+
+
 class SynthCircuit:
     """Random forward-solvable R1CS of the NZCP shape + Groth16 setup from explicit toxic waste (GPU)."""
 

@@ -540,7 +540,40 @@ static void synth_write_wtns_impl(const nzcp_synth* c, uint64_t wseed, uint8_t* 
 
 }  // namespace nzcp
 
+namespace nzcp {
+// n pseudo-random points k_i * G (k_i from splitmix64(seed)), Montgomery affine, written to a HOST buffer.
+template <class F>
+static void synth_points_impl(const Affine<F>& gen, uint64_t seed, size_t n, uint8_t* out) {
+  std::vector<Affine<F>> tab = fixed_base_table<F>(gen);
+  Affine<F>* d_tab = nullptr;
+  NZCP_CUDA(cudaMalloc(&d_tab, tab.size() * sizeof(Affine<F>)));
+  struct Free { void* p; ~Free() { cudaFree(p); } } fr{d_tab};
+  NZCP_CUDA(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(Affine<F>), cudaMemcpyHostToDevice));
+  Rng g(seed);
+  const size_t chunk = (size_t)1 << 20;
+  std::vector<Fr> sc;
+  for (size_t done = 0; done < n; done += chunk) {
+    size_t cnt = n - done < chunk ? n - done : chunk;
+    sc.resize(cnt);
+    for (size_t i = 0; i < cnt; i++) {
+      sc[i] = g.fr_plain();
+      if (sc[i].is_zero()) sc[i].v[0] = 1;
+    }
+    fixed_base_batch<F>(d_tab, sc, out + done * sizeof(Affine<F>));
+  }
+}
+}  // namespace nzcp
+
 extern "C" {
+
+int nzcp_synth_points(uint64_t seed, size_t n_points, int g2, int device, uint8_t* out) {
+  return api_guard([&] {
+    if (!out && n_points) throw ApiError(NZCP_E_ARG, "null argument");
+    use_device(device);
+    if (g2) synth_points_impl<Fq2>(g2_generator(), seed, n_points, out);
+    else synth_points_impl<Fq>(g1_generator(), seed, n_points, out);
+  });
+}
 
 int nzcp_synth_create(uint64_t seed, uint32_t n_constraints, uint32_t n_public, uint32_t n_free, nzcp_synth** out) {
   return api_guard([&] {
