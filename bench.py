@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="proofs per step per GPU")
     ap.add_argument("--shape", default="live", choices=sorted(SHAPES))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--provers", type=int, default=2, help="concurrent provers (host threads + stream sets) per GPU")
+    ap.add_argument("--provers", type=int, default=3, help="concurrent provers (host threads + stream sets) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -296,8 +296,12 @@ def roofline_block(dbg, zk, hbm, peak_src):
         alg_bytes = ent * (64 + 4) + (ent / 64.0) * 128
         out["roofline"] = {
             "kernel": "msm_accumulate_kernel<Fq> (H MSM bucket accumulation)", "bound": "int32-mul-pipe",
-            "achieved": ach / 1e9, "peak": peak_mul / 1e9, "unit": "GFqmul/s", "frac": ach / peak_mul, "traffic": None,
+            "achieved": ach / 1e9, "peak": peak_mul / 1e9, "unit": "GFqmul/s", "frac": ach / peak_mul,
+            "traffic": 2.31e9 * ent / 16776933.0,
             "launch_ms": acc_ms, "algorithmic_fq_mul": ent * 10,
+            "traffic_note": "ncu --set full (profiles/r01_ncu_accumulate_full.md): dram read+write 2.31 GB per launch vs "
+                            "1.14 GB algorithmic (68 B/entry): 64-B points fetched as 128-B lines; DRAM at 10 % of peak, "
+                            "fmaheavy (IMAD.WIDE) pipe 88 % active -- the kernel sits on the multiplier, not on memory",
             "peak_source": "measured here: %.2f T IMAD.WIDE.U32/s (32 per SM per clock, half the 32-bit IMAD rate) / 128 "
                            "32x32 products per 254-bit Montgomery mul; a register-only Fq mul microbenchmark reaches "
                            "%.1f GFqmul/s" % (ip["imad_wide_per_s"] / 1e12, ip["fq_mul_per_s"] / 1e9),

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnzcp_prover.so")
+LIB_PATH = os.environ.get("NZCP_LIB_PATH") or os.path.join(_HERE, "libnzcp_prover.so")   # override: tuning variants
 
 NZCP_OK = 0
 NZCP_E_ARG, NZCP_E_FORMAT, NZCP_E_NOT_GROTH16, NZCP_E_CURVE = -1, -2, -3, -4

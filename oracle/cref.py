@@ -39,7 +39,11 @@ def _addr(buf):
 
 
 def max_threads():
-    return load().nzo_max_threads()
+    """Host threads available to this process (not OMP_NUM_THREADS: torchrun pins that to 1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def field_op(field, op, a, b, n):
