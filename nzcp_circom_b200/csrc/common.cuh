@@ -90,6 +90,8 @@ struct MsmSort {
   size_t n_points = 0;
   int c = 0, n_windows = 0;
   size_t n_buckets = 0;     // 2^(c-1)
+  bool smem_hist = false;   // histogram in shared memory (<= 2^15 buckets) or with global atomics
+  uint32_t n_copies = 0;    // private copies of each bucket counter (smem path: one per block)
   uint32_t* counts = nullptr;
   uint32_t* offsets = nullptr;
   uint32_t* cursors = nullptr;

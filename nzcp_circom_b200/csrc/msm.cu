@@ -39,11 +39,13 @@ static constexpr int kHeavyTasks = 16;     // buckets with more tasks than this 
 static constexpr int kHeavyThreads = 128;
 static constexpr int kHeavyChunk = 512;     // task partials per stage-1 block of the heavy combine
 static constexpr int kGroupLog = 5;        // radix of the bucket-reduction tree (one warp per group)
-static constexpr int kCopiesLog = 4;       // 2^4 private copies of every bucket counter (spreads the L2 atomics)
-static constexpr int kCopies = 1 << kCopiesLog;
+static constexpr int kCopiesGlobal = 16;   // global-atomic histogram (c > 16): private copies of every bucket counter
+static constexpr int kSmemHistBuckets = 1 << 15;  // shared-memory histogram path: <= 2^15 buckets (128 KB), c <= 16
+static constexpr int kSmemHistThreads = 1024;
 static constexpr int kScanBlock = 1024;    // elements per block of the multi-block scan
 
 struct DigitParams {
+  uint32_t n_copies;  // private copies of every bucket counter (counter index = bucket * n_copies + copy)
   uint32_t n_points;  // scalars in this launch
   uint32_t stride;    // points per window of the table the entries index (>= n_points)
   int c;
@@ -110,9 +112,9 @@ msm_digits_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __res
       for (int k = 0; k < 8; k++) s[k] = 0;
     }
   }
-  // Counter (d-1) * kCopies + copy: a bucket's sub-ranges stay adjacent, so its entries are still one contiguous run.
+  // Counter (d-1) * n_copies + copy: a bucket's sub-ranges stay adjacent, so its entries are still one contiguous run.
   // Lanes of a warp that hit the same counter (the 0/1-heavy witness: digit 1 in window 0) are merged into one atomic.
-  const uint32_t copy = blockIdx.x & (kCopies - 1);
+  const uint32_t copy = blockIdx.x % p.n_copies;
   const uint32_t lane = threadIdx.x & 31;
   const unsigned active = 0xffffffffu;
   uint32_t carry = 0;
@@ -131,14 +133,78 @@ msm_digits_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __res
     const uint32_t leader = __ffs(peers) - 1;
     const uint32_t rank = __popc(peers & ((1u << lane) - 1));
     uint32_t base = 0;
-    if (d && lane == leader) base = atomicAdd(&counts_or_cursors[(d - 1) * kCopies + copy], (uint32_t)__popc(peers));
+    if (d && lane == leader) base = atomicAdd(&counts_or_cursors[(d - 1) * p.n_copies + copy], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     if (SCATTER && d) entries[base + rank] = ((uint32_t)w * p.stride + i) | (neg << 31);
   }
   if (!SCATTER && carry) atomicOr(&flags[1], 2u);
 }
 
-// Multi-block exclusive scan of the n_buckets * kCopies counters (3 launches: block sums, scan of the sums, rescan).
+// Shared-memory histogram variant (<= 2^15 buckets): one block per SM owns a contiguous chunk of the scalars and a
+// private 128 KB histogram, so the per-digit atomics never leave the SM.  COUNT writes its column of the
+// [bucket][block] counter matrix; after the scan SCATTER reloads that column as its private cursors, so the entries of
+// a bucket are ordered by block -- the layout (and the MSM result) is the same as with global atomics.
+template <bool SCATTER>
+__global__ void __launch_bounds__(kSmemHistThreads, 1)
+msm_digits_smem_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __restrict__ counts_or_offsets,
+                       uint32_t* __restrict__ entries, uint32_t* __restrict__ flags) {
+  extern __shared__ uint32_t hist[];
+  for (uint32_t b = threadIdx.x; b < p.n_buckets; b += blockDim.x)
+    hist[b] = SCATTER ? counts_or_offsets[b * p.n_copies + blockIdx.x] : 0u;
+  __syncthreads();
+  const uint32_t per_block = ((p.n_points + gridDim.x - 1) / gridDim.x + 31) & ~31u;   // whole warps stay together
+  const uint32_t begin = blockIdx.x * per_block;
+  const uint32_t end = begin + per_block < p.n_points ? begin + per_block : p.n_points;
+  uint32_t bad = 0;
+  for (uint32_t i0 = begin; i0 < end; i0 += blockDim.x) {
+    const uint32_t i = i0 + threadIdx.x;
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < end) {
+      const uint4* q = reinterpret_cast<const uint4*>(scalars + i);
+      uint4 a = __ldg(q), b = __ldg(q + 1);
+      s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+      s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+      bool ge = true;   // canonical (< r)?
+#pragma unroll
+      for (int k = 7; k >= 0; k--) {
+        uint32_t m = FrParams::mod(k);
+        if (s[k] != m) {
+          ge = s[k] > m;
+          break;
+        }
+      }
+      if (ge) {
+        bad |= 1u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = 0;
+      }
+    }
+    uint32_t carry = 0;
+    for (int w = 0; w < p.n_windows; w++) {
+      uint32_t d = scalar_bits(s, w * p.c, p.c) + carry;
+      uint32_t neg = 0;
+      if (d > p.n_buckets) {
+        d = (1u << p.c) - d;
+        neg = 1;
+        carry = 1;
+      } else {
+        carry = 0;
+      }
+      if (d) {   // shared-memory atomics: same-address lanes (the witness's digit 1) serialise on the SM, cheaply
+        const uint32_t pos = atomicAdd(&hist[d - 1], 1u);
+        if (SCATTER) entries[pos] = ((uint32_t)w * p.stride + i) | (neg << 31);
+      }
+    }
+    if (carry) bad |= 2u;
+  }
+  if (!SCATTER) {
+    if (bad) atomicOr(&flags[1], bad);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < p.n_buckets; b += blockDim.x) counts_or_offsets[b * p.n_copies + blockIdx.x] = hist[b];
+  }
+}
+
+// Multi-block exclusive scan of the n_buckets * n_copies counters (3 launches: block sums, scan of the sums, rescan).
 __global__ void __launch_bounds__(256) msm_scan_sums_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ sums, uint32_t n) {
   __shared__ uint32_t sh[8];
   uint32_t base = blockIdx.x * kScanBlock;
@@ -227,19 +293,20 @@ msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uin
   }
 }
 
-// Bucket totals from the scanned sub-counters: bcount[b] = offsets[(b+1)*kCopies] - offsets[b*kCopies].
+// Bucket totals from the scanned sub-counters: bcount[b] = offsets[(b+1)*n_copies] - offsets[b*n_copies].
 __global__ void __launch_bounds__(256)
-msm_bucket_count_kernel(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ bcount, uint32_t n_buckets) {
+msm_bucket_count_kernel(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ bcount, uint32_t n_buckets,
+                        uint32_t n_copies) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_buckets) return;
-  bcount[b] = offsets[(b + 1) * kCopies] - offsets[b * kCopies];
+  bcount[b] = offsets[(b + 1) * n_copies] - offsets[b * n_copies];
 }
 
 // One thread per task: find its bucket by binary search in task_off, then (first entry, length).
 __global__ void __launch_bounds__(256)
 msm_task_fill_kernel(const uint32_t* __restrict__ bcount, const uint32_t* __restrict__ offsets,
                      const uint32_t* __restrict__ task_off, uint2* __restrict__ tasks, uint32_t n_buckets,
-                     const uint32_t* __restrict__ flags) {
+                     uint32_t n_copies, const uint32_t* __restrict__ flags) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= flags[2]) return;
   const uint32_t tl = flags[4];
@@ -250,7 +317,7 @@ msm_task_fill_kernel(const uint32_t* __restrict__ bcount, const uint32_t* __rest
   }
   const uint32_t done = (t - task_off[lo]) * tl;
   const uint32_t left = bcount[lo] - done;
-  tasks[t] = make_uint2(offsets[lo * kCopies] + done, left < tl ? left : tl);
+  tasks[t] = make_uint2(offsets[lo * n_copies] + done, left < tl ? left : tl);
 }
 
 // ------------------------------------------------------------------------------------------------ run
@@ -503,12 +570,22 @@ void msm_sort_create(MsmSort* s, size_t n_points, int c) {
   if (max_entries / kTaskLenMin < by_target) by_target = max_entries / kTaskLenMin;
   s->max_tasks = s->n_buckets + (by_len > by_target ? by_len : by_target) + 1;
   size_t tot = 0;
-  size_t n_ctr = s->n_buckets * kCopies;
+  s->smem_hist = s->n_buckets <= (size_t)kSmemHistBuckets;
+  s->n_copies = s->smem_hist ? 148 : kCopiesGlobal;
+  size_t n_ctr = s->n_buckets * s->n_copies;
   s->counts = dev_alloc<uint32_t>(n_ctr + 1, &tot);
   s->offsets = dev_alloc<uint32_t>(n_ctr + 1, &tot);
   s->cursors = dev_alloc<uint32_t>(n_ctr + 1, &tot);
   s->bcount = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
   s->block_sums = dev_alloc<uint32_t>(2 * (n_ctr / kScanBlock + 2), &tot);
+  if (s->smem_hist) {
+    static bool attr = false;
+    if (!attr) {
+      NZCP_CUDA(cudaFuncSetAttribute(msm_digits_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHistBuckets * 4));
+      NZCP_CUDA(cudaFuncSetAttribute(msm_digits_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHistBuckets * 4));
+      attr = true;
+    }
+  }
   s->entries = dev_alloc<uint32_t>(max_entries, &tot);
   s->task_off = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
   s->tasks = dev_alloc<uint2>(s->max_tasks, &tot);
@@ -535,33 +612,49 @@ void msm_sort_destroy(MsmSort* s) {
 void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_t st) {
   if (n_points > s->n_points) throw std::runtime_error("msm: sort plan too small");
   const uint32_t nb = (uint32_t)s->n_buckets;
-  const uint32_t n_ctr = nb * kCopies;
-  NZCP_CUDA(cudaMemsetAsync(s->counts, 0, (n_ctr + 1) * sizeof(uint32_t), st));
   NZCP_CUDA(cudaMemsetAsync(s->flags, 0, 8 * sizeof(uint32_t), st));
   if (n_points) {
+    // shared-memory histogram: one block per SM (fewer for small inputs); otherwise 16 global copies of the counters
+    uint32_t n_copies = s->n_copies;
+    if (s->smem_hist) {
+      uint32_t want = div_up(n_points, kSmemHistThreads);
+      if (want < n_copies) n_copies = want;
+    }
+    const uint32_t n_ctr = nb * n_copies;
     // entries index the table of the plan's full point count, so a shorter scalar vector still addresses T[w][i]
-    DigitParams dp{(uint32_t)n_points, (uint32_t)s->n_points, s->c, s->n_windows, nb};
-    unsigned gp = div_up(n_points, 256);
-    msm_digits_kernel<false><<<gp, 256, 0, st>>>(scalars, dp, s->counts, nullptr, s->flags);
+    DigitParams dp{n_copies, (uint32_t)n_points, (uint32_t)s->n_points, s->c, s->n_windows, nb};
+    const unsigned gp = div_up(n_points, 256);
+    const size_t hist_bytes = (size_t)nb * sizeof(uint32_t);
+    if (s->smem_hist) {
+      NZCP_CUDA(cudaMemsetAsync(s->counts + n_ctr, 0, sizeof(uint32_t), st));
+      msm_digits_smem_kernel<false><<<n_copies, kSmemHistThreads, hist_bytes, st>>>(scalars, dp, s->counts, nullptr, s->flags);
+    } else {
+      NZCP_CUDA(cudaMemsetAsync(s->counts, 0, (n_ctr + 1) * sizeof(uint32_t), st));
+      msm_digits_kernel<false><<<gp, 256, 0, st>>>(scalars, dp, s->counts, nullptr, s->flags);
+    }
     NZCP_LAUNCH_CHECK();
     // exclusive scan of the sub-counters (counts[n_ctr] = 0 is scanned too, so offsets[n_ctr] = total)
     const uint32_t n_scan = n_ctr + 1;
     const uint32_t n_blk = div_up(n_scan, kScanBlock);
     uint32_t* blk_sum = s->block_sums;
-    uint32_t* blk_off = s->block_sums + (n_ctr / kScanBlock + 2);
+    uint32_t* blk_off = s->block_sums + (s->n_buckets * s->n_copies / kScanBlock + 2);
     msm_scan_sums_kernel<<<n_blk, 256, 0, st>>>(s->counts, blk_sum, n_scan);
     NZCP_LAUNCH_CHECK();
     msm_scan_kernel<false><<<1, 1024, 0, st>>>(blk_sum, blk_off, n_blk, s->flags + 3, s->flags);
     NZCP_LAUNCH_CHECK();
-    msm_scan_apply_kernel<<<n_blk, 256, 0, st>>>(s->counts, blk_off, s->offsets, s->cursors, n_scan);
+    msm_scan_apply_kernel<<<n_blk, 256, 0, st>>>(s->counts, blk_off, s->offsets, s->smem_hist ? nullptr : s->cursors, n_scan);
     NZCP_LAUNCH_CHECK();
-    msm_digits_kernel<true><<<gp, 256, 0, st>>>(scalars, dp, s->cursors, s->entries, s->flags);
+    if (s->smem_hist)
+      msm_digits_smem_kernel<true><<<n_copies, kSmemHistThreads, hist_bytes, st>>>(scalars, dp, s->offsets, s->entries, s->flags);
+    else
+      msm_digits_kernel<true><<<gp, 256, 0, st>>>(scalars, dp, s->cursors, s->entries, s->flags);
     NZCP_LAUNCH_CHECK();
-    msm_bucket_count_kernel<<<div_up(nb, 256), 256, 0, st>>>(s->offsets, s->bcount, nb);
+    msm_bucket_count_kernel<<<div_up(nb, 256), 256, 0, st>>>(s->offsets, s->bcount, nb, n_copies);
     NZCP_LAUNCH_CHECK();
     msm_scan_kernel<true><<<1, 1024, 0, st>>>(s->bcount, s->task_off, nb, s->flags + 2, s->flags);
     NZCP_LAUNCH_CHECK();
-    msm_task_fill_kernel<<<div_up(s->max_tasks, 256), 256, 0, st>>>(s->bcount, s->offsets, s->task_off, s->tasks, nb, s->flags);
+    msm_task_fill_kernel<<<div_up(s->max_tasks, 256), 256, 0, st>>>(s->bcount, s->offsets, s->task_off, s->tasks, nb, n_copies,
+                                                                     s->flags);
     NZCP_LAUNCH_CHECK();
   } else {
     NZCP_CUDA(cudaMemsetAsync(s->task_off, 0, (nb + 1) * sizeof(uint32_t), st));
