@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="proofs per step per GPU")
+    ap.add_argument("--batch", type=int, default=12, help="proofs per step per GPU")
     ap.add_argument("--shape", default="live", choices=sorted(SHAPES))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--provers", type=int, default=3, help="concurrent provers (host threads + stream sets) per GPU")

@@ -226,3 +226,23 @@ def test_full_size_proof_verifies_and_matches_closed_form(lib, nc, npub, nfree):
     assert out2["proof"] != out["proof"]
     assert groth16.verify(vk, out2["publicSignals"], out2["proof"])
     groth16.terminate()
+
+
+def test_prover_pool_matches_single_prover(lib):
+    """Several proofs in flight on one GPU (host threads + per-prover streams) give the same bytes as one at a time."""
+    sc = api.SynthCircuit(seed=5, n_constraints=3000, n_public=9, n_free=64)
+    zb = sc.zkey([TOXIC[k] for k in ("tau", "alpha", "beta", "gamma", "delta")])
+    wl = [sc.wtns(100 + k) for k in range(7)]
+    with api.Zkey(zb) as zk:
+        with api.Prover(zk) as pr:
+            single = [pr.prove(w, r=3 + k, s=5 + k)["proof"] for k, w in enumerate(wl)]
+        with api.ProverPool(zk, 3) as pool:
+            many = [pool.provers[k % 3].prove(w, r=3 + k, s=5 + k)["proof"] for k, w in enumerate(wl)]
+            same_rs = pool.prove_many(wl, r=11, s=13)
+        assert many == single
+        with api.Prover(zk) as pr:
+            assert [x["proof"] for x in same_rs] == [pr.prove(w, r=11, s=13)["proof"] for w in wl]
+    vk = groth16.exportVerificationKey(zb)
+    out = groth16.prove({"type": "mem", "data": zb}, {"type": "mem", "data": wl[0]}, r=11, s=13)
+    assert groth16.verify(vk, out["publicSignals"], out["proof"])
+    groth16.terminate()
