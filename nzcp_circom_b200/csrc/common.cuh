@@ -116,14 +116,14 @@ struct MsmRun {
   bool g2 = false;
   void* partial = nullptr;
   void* buckets = nullptr;
-  void* lvl_a[2] = {nullptr, nullptr};
-  void* lvl_r[2] = {nullptr, nullptr};
+  void* marg = nullptr;       // marginal bucket sums M_k[j], k < n_digits, j < 32
+  int n_digits = 0;           // base-32 digits of a bucket id
   uint32_t* heavy_list = nullptr;
   uint32_t* heavy_count = nullptr;   // [0] heavy buckets, [1] heavy chunks
   uint32_t* chunk_cnt = nullptr;
   uint32_t* chunk_off = nullptr;
   void* chunk_partial = nullptr;
-  void* out = nullptr;        // device: A_top, R_top
+  void* out = nullptr;        // device: S_0 .. S_{n_digits-1}, T
   void* out_host = nullptr;   // pinned
   cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;  // around the accumulate kernel (roofline timing)
   size_t scratch_bytes = 0;

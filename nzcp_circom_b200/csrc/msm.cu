@@ -21,9 +21,10 @@
 //   run (per base section):
 //     5 accumulate     one thread per task: XYZZ accumulator in registers, 8M+2S mixed adds, table entries gathered
 //                      by index with the next one prefetched into L1 during the current add
-//     6 combine        one warp per bucket sums its tasks (shuffle tree); a block per bucket for the few huge ones
-//     7 reduce         sum_v v * B_v by a radix-32 tree: per group a warp does a suffix scan + tree sum with shuffles
-//     8 host           R_top + A_top, one group addition
+//     6 combine        one thread per bucket sums its (<= 16) task partials; buckets with more go through a two-stage
+//                      block-wide sum (chunks of 512 partials, then the chunk results)
+//     7 reduce         sum_v v * B_v through marginal sums per base-32 digit of the bucket id (two launches, no level tree)
+//     8 host           T + sum_k 32^k S_k: ten doublings and four additions
 #include "common.cuh"
 
 #ifndef NZCP_G2_ACC_BLOCKS
@@ -38,7 +39,7 @@ static constexpr int kTargetTasks = 148 * 640;  // resident accumulate threads o
 static constexpr int kHeavyTasks = 16;     // buckets with more tasks than this go to the block-wide combine
 static constexpr int kHeavyThreads = 128;
 static constexpr int kHeavyChunk = 512;     // task partials per stage-1 block of the heavy combine
-static constexpr int kGroupLog = 5;        // radix of the bucket-reduction tree (one warp per group)
+static constexpr int kMaxDigits = 4;        // base-32 digits of a bucket id (c <= 20)
 static constexpr int kCopiesGlobal = 16;   // global-atomic histogram (c > 16): private copies of every bucket counter
 static constexpr int kSmemHistBuckets = 1 << 15;  // shared-memory histogram path: <= 2^15 buckets (128 KB), c <= 16
 static constexpr int kSmemHistThreads = 1024;
@@ -401,7 +402,7 @@ template <class F>
 __device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F> acc, XYZZ<F>* sm) {
   sm[threadIdx.x] = acc;
   __syncthreads();
-  for (uint32_t stride = kHeavyThreads / 2; stride >= 1; stride >>= 1) {
+  for (uint32_t stride = blockDim.x / 2; stride >= 1; stride >>= 1) {
     if (threadIdx.x < stride) {
       XYZZ<F> a = sm[threadIdx.x];
       xyzz_add(a, sm[threadIdx.x + stride]);
@@ -459,45 +460,52 @@ msm_combine_heavy2_kernel(const uint32_t* __restrict__ heavy_list, const uint32_
   }
 }
 
-// One level of the bucket-reduction tree, one warp per group of G = 2^g_log inputs carrying weights 0..G-1:
-//   A = sum_j P[j]                       (lane 0 of a suffix scan:  run_j = sum_{k>=j} P[k])
-//   S = sum_j j * P[j] = sum_{j>=1} run_j (tree sum over lanes)
-//   R = sum_j Rin[j] + 2^shift * S       (Rin = weighted sums of the children's own subtrees; absent at level 1)
-// At the top  sum_v v * B_v = R_top + A_top  (bucket id v-1 carries weight v-1, plus one A_top).
+// Bucket reduction  sum_v v * B_v  without a dependent tree of levels.  Write the bucket id v-1 in base 32,
+// v-1 = sum_k d_k 32^k.  Then  sum_v (v-1) B_v = sum_k 32^k * sum_j j * M_k[j]  with the marginal sums
+// M_k[j] = sum of all buckets whose k-th digit is j.  Stage 1 computes every M_k[j] as an independent block-wide tree
+// sum (fully parallel, chain ~ log); stage 2 turns each digit's 32 marginals into sum_j j M_k[j] with one warp
+// (suffix scan + tree sum through shuffles); the host finishes with  T + sum_k 32^k S_k  (T = sum of all buckets).
+static constexpr int kMargThreads = 128;
+
 template <class F>
-__global__ void __launch_bounds__(128)
-msm_reduce_level_kernel(const XYZZ<F>* __restrict__ in_a, const XYZZ<F>* __restrict__ in_r, XYZZ<F>* __restrict__ out_a,
-                        XYZZ<F>* __restrict__ out_r, uint32_t n_groups, int g_log, int shift) {
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (g >= n_groups) return;
-  const uint32_t G = 1u << g_log;
-  const size_t base = (size_t)g << g_log;
-  XYZZ<F> run = lane < G ? in_a[base + lane] : XYZZ<F>::inf();
-  for (uint32_t d = 1; d < G; d <<= 1) {
+__global__ void __launch_bounds__(kMargThreads)
+msm_marginal_kernel(const XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ marg, uint32_t bits) {
+  extern __shared__ unsigned char heavy_sm_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_sm_raw);
+  const uint32_t k = blockIdx.x >> 5, j = blockIdx.x & 31;      // digit position, digit value
+  const uint32_t lo_bits = 5 * k;
+  const uint32_t dig_bits = bits - lo_bits < 5 ? bits - lo_bits : 5;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (j < (1u << dig_bits)) {
+    const uint32_t count = 1u << (bits - dig_bits);              // buckets with d_k == j
+    const uint32_t lo_mask = (1u << lo_bits) - 1;
+    for (uint32_t idx = threadIdx.x; idx < count; idx += blockDim.x) {
+      const uint32_t v = (idx & lo_mask) | (j << lo_bits) | ((idx >> lo_bits) << (lo_bits + dig_bits));
+      xyzz_add(acc, buckets[v]);
+    }
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) marg[blockIdx.x] = acc;
+}
+
+// One warp per digit position: out[k] = sum_j j * M_k[j]; warp 0 also writes the total T = sum_j M_0[j] to out[n_digits].
+template <class F>
+__global__ void __launch_bounds__(32)
+msm_weighted_kernel(const XYZZ<F>* __restrict__ marg, XYZZ<F>* __restrict__ out, uint32_t n_digits) {
+  const uint32_t k = blockIdx.x, lane = threadIdx.x;
+  XYZZ<F> run = marg[k * 32 + lane];                             // marginals beyond the digit's range are infinity
+  for (uint32_t d = 1; d < 32; d <<= 1) {
     XYZZ<F> o = shfl_down_obj(run, d);
-    if (lane + d < G) xyzz_add(run, o);
+    if (lane + d < 32) xyzz_add(run, o);
   }
-  XYZZ<F> leaf = (lane >= 1 && lane < G) ? run : XYZZ<F>::inf();
+  XYZZ<F> leaf = lane >= 1 ? run : XYZZ<F>::inf();              // sum_{j>=1} suffix_j = sum_j j M[j]
   for (uint32_t off = 16; off >= 1; off >>= 1) {
-    if (off < G) {
-      XYZZ<F> o = shfl_down_obj(leaf, off);
-      xyzz_add(leaf, o);
-    }
-  }
-  for (int k = 0; k < shift; k++) leaf = xyzz_dbl(leaf);
-  if (in_r) {
-    XYZZ<F> r = lane < G ? in_r[base + lane] : XYZZ<F>::inf();
-    for (uint32_t off = 16; off >= 1; off >>= 1) {
-      if (off < G) {
-        XYZZ<F> o = shfl_down_obj(r, off);
-        xyzz_add(r, o);
-      }
-    }
-    xyzz_add(leaf, r);
+    XYZZ<F> o = shfl_down_obj(leaf, off);
+    xyzz_add(leaf, o);
   }
   if (lane == 0) {
-    out_a[g] = run;
-    out_r[g] = leaf;
+    out[k] = leaf;
+    if (k == 0) out[n_digits] = run;
   }
 }
 
@@ -674,19 +682,16 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
   size_t tot = 0;
   r->partial = dev_alloc<unsigned char>(sort->max_tasks * psz, &tot);
   r->buckets = dev_alloc<unsigned char>(sort->n_buckets * psz, &tot);
-  size_t lvl = (sort->n_buckets >> 1) + 1;
-  for (int i = 0; i < 2; i++) {
-    r->lvl_a[i] = dev_alloc<unsigned char>(lvl * psz, &tot);
-    r->lvl_r[i] = dev_alloc<unsigned char>(lvl * psz, &tot);
-  }
+  r->marg = dev_alloc<unsigned char>(kMaxDigits * 32 * psz, &tot);
   r->heavy_list = dev_alloc<uint32_t>(sort->n_buckets, &tot);
   r->heavy_count = dev_alloc<uint32_t>(2, &tot);
   r->chunk_cnt = dev_alloc<uint32_t>(sort->n_buckets + 1, &tot);
   r->chunk_off = dev_alloc<uint32_t>(sort->n_buckets + 1, &tot);
   r->chunk_partial = dev_alloc<unsigned char>((sort->max_tasks / kHeavyChunk + sort->n_buckets + 1) * psz, &tot);
-  r->out = dev_alloc<unsigned char>(2 * psz, &tot);
-  NZCP_CUDA(cudaMallocHost(&r->out_host, 2 * psz));
-  memset(r->out_host, 0, 2 * psz);
+  r->out = dev_alloc<unsigned char>((kMaxDigits + 1) * psz, &tot);
+  NZCP_CUDA(cudaMallocHost(&r->out_host, (kMaxDigits + 1) * psz));
+  memset(r->out_host, 0, (kMaxDigits + 1) * psz);
+  r->n_digits = (sort->c - 1 + 4) / 5;
   NZCP_CUDA(cudaEventCreate(&r->ev_acc0));
   NZCP_CUDA(cudaEventCreate(&r->ev_acc1));
   r->scratch_bytes = tot;
@@ -695,10 +700,7 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
 void msm_run_destroy(MsmRun* r) {
   cudaFree(r->partial);
   cudaFree(r->buckets);
-  for (int i = 0; i < 2; i++) {
-    cudaFree(r->lvl_a[i]);
-    cudaFree(r->lvl_r[i]);
-  }
+  cudaFree(r->marg);
   cudaFree(r->heavy_list);
   cudaFree(r->heavy_count);
   cudaFree(r->chunk_cnt);
@@ -739,27 +741,14 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
   msm_combine_heavy2_kernel<F><<<148, kHeavyThreads, kHeavyThreads * psz, st>>>(r->heavy_list, r->heavy_count, r->chunk_off,
                                                                                 chunk_partial, buckets);
   NZCP_LAUNCH_CHECK();
-  int bits_left = s->c - 1, shift = 0, level = 0;
-  const XYZZ<F>* in_a = buckets;
-  const XYZZ<F>* in_r = nullptr;
-  size_t groups_in = nb;
-  while (bits_left > 0) {
-    int g_log = bits_left < kGroupLog ? bits_left : kGroupLog;
-    size_t n_groups = groups_in >> g_log;
-    bool last = (bits_left == g_log);
-    XYZZ<F>* out_a = last ? out : reinterpret_cast<XYZZ<F>*>(r->lvl_a[level & 1]);
-    XYZZ<F>* out_r = last ? out + 1 : reinterpret_cast<XYZZ<F>*>(r->lvl_r[level & 1]);
-    msm_reduce_level_kernel<F><<<div_up(n_groups * 32, 128), 128, 0, st>>>(in_a, in_r, out_a, out_r, (uint32_t)n_groups,
-                                                                          g_log, shift);
-    NZCP_LAUNCH_CHECK();
-    in_a = out_a;
-    in_r = out_r;
-    groups_in = n_groups;
-    shift += g_log;
-    bits_left -= g_log;
-    level++;
-  }
-  NZCP_CUDA(cudaMemcpyAsync(r->out_host, r->out, 2 * psz, cudaMemcpyDeviceToHost, st));
+  const uint32_t bits = (uint32_t)(s->c - 1);
+  const uint32_t n_digits = (bits + 4) / 5;
+  XYZZ<F>* marg = reinterpret_cast<XYZZ<F>*>(r->marg);
+  msm_marginal_kernel<F><<<n_digits * 32, kMargThreads, kMargThreads * psz, st>>>(buckets, marg, bits);
+  NZCP_LAUNCH_CHECK();
+  msm_weighted_kernel<F><<<n_digits, 32, 0, st>>>(marg, out, n_digits);
+  NZCP_LAUNCH_CHECK();
+  NZCP_CUDA(cudaMemcpyAsync(r->out_host, r->out, (n_digits + 1) * psz, cudaMemcpyDeviceToHost, st));
 }
 
 void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaStream_t st) {
@@ -769,6 +758,8 @@ void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaS
                                    (int)(kHeavyThreads * sizeof(G2XYZZ))));
     NZCP_CUDA(cudaFuncSetAttribute(msm_combine_heavy2_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kHeavyThreads * sizeof(G2XYZZ))));
+    NZCP_CUDA(cudaFuncSetAttribute(msm_marginal_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kMargThreads * sizeof(G2XYZZ))));
     attr_done = true;
   }
   if (r->g2 != table->g2) throw std::runtime_error("msm: run and table group mismatch");
@@ -780,9 +771,15 @@ void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaS
 
 template <class F>
 static XYZZ<F> msm_run_finish_t(const MsmRun* r) {
+  // sum_v v B_v = T + sum_k 32^k S_k : Horner over the digit positions (a handful of host group operations)
   const XYZZ<F>* w = reinterpret_cast<const XYZZ<F>*>(r->out_host);
-  XYZZ<F> acc = w[0];
-  xyzz_add(acc, w[1]);
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int k = r->n_digits - 1; k >= 0; k--) {
+    if (!acc.is_inf())
+      for (int d = 0; d < 5; d++) acc = xyzz_dbl(acc);
+    xyzz_add(acc, w[k]);
+  }
+  xyzz_add(acc, w[r->n_digits]);
   return acc;
 }
 

@@ -22,7 +22,7 @@ def proof_slice():
     st = rows[j]["Stream"]
     e = j
     for k in range(j, len(rows)):
-        if rows[k]["Stream"] == st and "msm_reduce_level" in rows[k]["Kernel Name"]:
+        if rows[k]["Stream"] == st and "msm_weighted_kernel" in rows[k]["Kernel Name"]:
             e = k
         if "intpipe" in rows[k]["Kernel Name"]:
             break
@@ -30,11 +30,11 @@ def proof_slice():
     pj = prev_join
     pe = pj
     for k in range(pj, j):
-        if rows[k]["Stream"] == st and "msm_reduce_level" in rows[k]["Kernel Name"]:
+        if rows[k]["Stream"] == st and "msm_weighted_kernel" in rows[k]["Kernel Name"]:
             pe = k
             break
     # previous H msm end = last reduce on st before last_join
-    pe = max(k for k in range(pj, j) if rows[k]["Stream"] == st and "msm_reduce_level" in rows[k]["Kernel Name"])
+    pe = max(k for k in range(pj, j) if rows[k]["Stream"] == st and "msm_weighted_kernel" in rows[k]["Kernel Name"])
     return rows[pe + 1:e + 1]
 sl = proof_slice()
 agg = collections.OrderedDict()
