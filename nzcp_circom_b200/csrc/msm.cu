@@ -385,17 +385,39 @@ msm_combine_kernel(const uint32_t* __restrict__ task_off, const XYZZ<F>* __restr
 // Heavy buckets (more than kHeavyTasks task partials; the witness's bucket "1" has ~15 000) are summed in two stages
 // so that no single block walks a long dependent chain: stage 1 reduces chunks of kHeavyChunk partials (one block per
 // chunk, all chunks of all heavy buckets in one grid), stage 2 sums each bucket's chunk results.
-__global__ void __launch_bounds__(256)
-msm_heavy_prepare_kernel(const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ heavy_list,
-                         const uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ chunk_cnt, uint32_t n_buckets) {
-  uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= n_buckets) return;
-  uint32_t v = 0;
-  if (h < *heavy_count) {
-    uint32_t b = heavy_list[h];
-    v = (task_off[b + 1] - task_off[b] + kHeavyChunk - 1) / kHeavyChunk;
+// chunk_off[h] = exclusive prefix of ceil(tasks(heavy bucket h) / kHeavyChunk), h <= n_heavy.  One block; the heavy
+// list is short (a few hundred buckets for the witness, none for dense scalars).
+__global__ void __launch_bounds__(1024)
+msm_heavy_scan_kernel(const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ heavy_list,
+                      uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ chunk_off) {
+  __shared__ uint32_t sums[1024];
+  const uint32_t n = heavy_count[0];
+  const uint32_t per = (n + 1023) / 1024;
+  const uint32_t b = threadIdx.x * per;
+  const uint32_t e = b + per < n ? b + per : n;
+  auto chunks = [&](uint32_t h) {
+    uint32_t bk = heavy_list[h];
+    return (task_off[bk + 1] - task_off[bk] + kHeavyChunk - 1) / kHeavyChunk;
+  };
+  uint32_t acc = 0;
+  for (uint32_t h = b; h < e; h++) acc += chunks(h);
+  sums[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    uint32_t v = threadIdx.x >= (uint32_t)off ? sums[threadIdx.x - off] : 0;
+    __syncthreads();
+    sums[threadIdx.x] += v;
+    __syncthreads();
   }
-  chunk_cnt[h] = v;
+  uint32_t run = threadIdx.x ? sums[threadIdx.x - 1] : 0;
+  for (uint32_t h = b; h < e; h++) {
+    chunk_off[h] = run;
+    run += chunks(h);
+  }
+  if (threadIdx.x == 1023) {
+    chunk_off[n] = sums[1023];
+    heavy_count[1] = sums[1023];
+  }
 }
 
 template <class F>
@@ -730,9 +752,7 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
   msm_combine_kernel<F><<<div_up(nb, 128), 128, 0, st>>>(s->task_off, partial, buckets, nb, r->heavy_list,
                                                                      r->heavy_count);
   NZCP_LAUNCH_CHECK();
-  msm_heavy_prepare_kernel<<<div_up(nb, 256), 256, 0, st>>>(s->task_off, r->heavy_list, r->heavy_count, r->chunk_cnt, nb);
-  NZCP_LAUNCH_CHECK();
-  msm_scan_kernel<false><<<1, 1024, 0, st>>>(r->chunk_cnt, r->chunk_off, nb, r->heavy_count + 1, nullptr);
+  msm_heavy_scan_kernel<<<1, 1024, 0, st>>>(s->task_off, r->heavy_list, r->heavy_count, r->chunk_off);
   NZCP_LAUNCH_CHECK();
   XYZZ<F>* chunk_partial = reinterpret_cast<XYZZ<F>*>(r->chunk_partial);
   msm_combine_heavy_kernel<F><<<296, kHeavyThreads, kHeavyThreads * psz, st>>>(s->task_off, partial, r->heavy_list,
