@@ -140,10 +140,30 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "p50_latency_ms": 1e3 * statistics.median(times), "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything except the final JSON line goes to stderr: NCCL prints its version banner on fd 1, and the driver
+    reads ONE JSON line from stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -268,7 +288,7 @@ def main():
                                               "of snarkjs groth16.prove (oracle/c), OpenMP; NOT snarkjs itself",
                                     "stage_sec": stages}
             line["proof_matches_cpu_port"] = correct
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
