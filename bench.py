@@ -9,8 +9,8 @@ compiled here: no circom / sha256-var-circom).  A step = B indepen
 resident proving key).  Multi-GPU = batch sharding, no collective (weak scaling: B proofs per rank per step).
 
 `value`  : proofs/s with the witnesses already resident in HBM (nzcp_prove_device).
-`e2e`    : proofs/s through the reference-facing call (nzcp_prove: a .wtns image in pinned HOST memory in, the proof
-           in host memory out; H2D + D2H inside the timed region).
+`e2e`    : proofs/s through the reference-facing call (nzcp_prove_batch: .wtns images in pinned HOST memory in, the
+           proofs in host memory out; H2D + D2H inside the timed region).
 `roofline`: the dominant kernel of the step, timed live with CUDA events on its own stream inside the library.
 `cpu_baseline` / `--impl reference`: the C restatement of snarkjs groth16.prove (oracle/c) on the host cores -- NOT
            snarkjs itself (node is not installed on these boxes); labelled kind="port".
@@ -220,7 +220,8 @@ def main():
     host_wtns = [p.numpy() for p in pinned]
 
     def step_e2e(record):
-        pool.prove_many(host_wtns, r=R_FIXED, s=S_FIXED)
+        # the reference-facing C-ABI call: host .wtns images in, proofs out, the library's own prover threads
+        zk.prove_batch(host_wtns, [R_FIXED] * B, [S_FIXED] * B, n_provers=args.provers)
 
     def latency_run(count):
         # p50 per-proof latency: one proof at a time through the host-buffer call, nothing else in flight

@@ -90,6 +90,12 @@ void nzcp_prover_free(nzcp_prover* p);
  * from the OS CSPRNG as snarkjs's Fr.random() does.  `dbg` may be NULL. */
 int nzcp_prove(nzcp_prover* p, const uint8_t* wtns, size_t wtns_len, const uint8_t* r, const uint8_t* s,
                nzcp_proof* proof, nzcp_prove_debug* dbg);
+/* Throughput mode (SURVEY.md 8e batch mode on one GPU): n_proofs independent .wtns images against one resident key, proved by
+ * `n_provers` host threads (0 = 3), each with its own prover (stream set + work buffers, kept in the key between calls), so
+ * that the latency-bound tail of one proof overlaps the multiplier-bound kernels of the next.  r, s: n_proofs x 32 bytes or
+ * NULL (random).  status (optional): per-proof return code.  Returns the first failure's code, or NZCP_OK. */
+int nzcp_prove_batch(nzcp_zkey* zk, const uint8_t* const* wtns, const size_t* wtns_len, size_t n_proofs, const uint8_t* r,
+                     const uint8_t* s, nzcp_proof* proofs, int n_provers, int* status);
 /* Same, but the witness is a bare array of n_vars 32-byte LE values (section 2 of a .wtns). */
 int nzcp_prove_witness(nzcp_prover* p, const uint8_t* witness, uint32_t n_witness, const uint8_t* r, const uint8_t* s,
                        nzcp_proof* proof, nzcp_prove_debug* dbg);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "nzcp_prover_create": (C.c_int, [_P, C.POINTER(_P)]),
     "nzcp_prover_free": (None, [_P]),
     "nzcp_prove": (C.c_int, [_P, _U8P, C.c_size_t, _U8P, _U8P, C.POINTER(Proof), C.POINTER(ProveDebug)]),
+    "nzcp_prove_batch": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, _U8P, _U8P,
+                                   C.POINTER(Proof), C.c_int, C.POINTER(C.c_int)]),
     "nzcp_prove_witness": (C.c_int, [_P, _U8P, C.c_uint32, _U8P, _U8P, C.POINTER(Proof), C.POINTER(ProveDebug)]),
     "nzcp_prove_device": (C.c_int, [_P, _P, _U8P, _U8P, C.POINTER(Proof), C.POINTER(ProveDebug)]),
     "nzcp_prover_witness_buffer": (_P, [_P]),

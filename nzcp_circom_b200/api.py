@@ -59,6 +59,19 @@ class Zkey:
         self.power, self.n_coefs, self.device_bytes = inf.power, inf.n_coefs, inf.device_bytes
         self._info = inf
 
+    def prove_batch(self, wtns_list, r_list=None, s_list=None, n_provers=0):
+        """nzcp_prove_batch: all proofs of the list through the library's own thread pool -> list of 256-byte proofs."""
+        n = len(wtns_list)
+        datas = [_as_bytes_like(w) for w in wtns_list]
+        ptrs = (C.c_void_p * n)(*[addr(d) for d in datas])
+        lens = (C.c_size_t * n)(*[_nbytes(d) for d in datas])
+        rb = b"".join(_scalar32(x) for x in r_list) if r_list is not None else None
+        sb = b"".join(_scalar32(x) for x in s_list) if s_list is not None else None
+        proofs = (Proof * n)()
+        status = (C.c_int * n)()
+        check(_lib.load().nzcp_prove_batch(self._h, ptrs, lens, n, addr(rb), addr(sb), proofs, int(n_provers), status))
+        return [bytes(p.pi_a) + bytes(p.pi_b) + bytes(p.pi_c) for p in proofs]
+
     def header_points(self):
         """alpha1, beta1, delta1 (64 B) and beta2, gamma2, delta2 (128 B): plain affine LE bytes."""
         i = self._info

@@ -9,6 +9,7 @@
 // concurrently with the H pipeline.
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "api_util.cuh"
 
@@ -64,6 +65,8 @@ using namespace nzcp;
 
 struct nzcp_zkey {
   int device = 0;
+  std::mutex pool_mu;                    // guards `pool` (provers owned by the key, used by nzcp_prove_batch)
+  std::vector<nzcp_prover*> pool;
   uint32_t n_vars = 0, n_public = 0, domain_size = 0, power = 0;
   uint64_t n_coefs = 0;
   G1Affine alpha1, beta1, delta1;  // Montgomery affine, as stored
@@ -90,9 +93,13 @@ struct nzcp_prover {
 
 namespace nzcp {
 
+static void prover_release(nzcp_prover* p);
+
 static void zkey_release(nzcp_zkey* zk) {
   if (!zk) return;
   cudaSetDevice(zk->device);
+  for (nzcp_prover* p : zk->pool) prover_release(p);
+  zk->pool.clear();
   cudaFree(zk->r1cs.row_ptr);
   cudaFree(zk->r1cs.col);
   cudaFree(zk->r1cs.val);
@@ -477,5 +484,48 @@ int nzcp_prove_device(nzcp_prover* p, const void* d_witness, const uint8_t* r, c
 void* nzcp_prover_witness_buffer(nzcp_prover* p) { return p ? p->d_wtns : nullptr; }
 
 uint64_t nzcp_prover_launch_count(const nzcp_prover*) { return g_launch_count.load(); }
+
+int nzcp_prove_batch(nzcp_zkey* zk, const uint8_t* const* wtns, const size_t* wtns_len, size_t n_proofs, const uint8_t* r,
+                     const uint8_t* s, nzcp_proof* proofs, int n_provers, int* status) {
+  return api_guard([&] {
+    if (!zk || (n_proofs && (!wtns || !wtns_len || !proofs))) throw ApiError(NZCP_E_ARG, "null argument");
+    if (n_provers < 1) n_provers = 3;
+    if ((size_t)n_provers > n_proofs) n_provers = (int)(n_proofs ? n_proofs : 1);
+    std::vector<nzcp_prover*> mine;
+    {
+      std::lock_guard<std::mutex> lk(zk->pool_mu);   // take provers out of the key's pool (created on first use)
+      while ((int)mine.size() < n_provers && !zk->pool.empty()) {
+        mine.push_back(zk->pool.back());
+        zk->pool.pop_back();
+      }
+    }
+    struct Return {
+      nzcp_zkey* zk; std::vector<nzcp_prover*>* v;
+      ~Return() { std::lock_guard<std::mutex> lk(zk->pool_mu); for (auto* p : *v) zk->pool.push_back(p); }
+    } ret{zk, &mine};
+    while ((int)mine.size() < n_provers) mine.push_back(prover_create_impl(zk));
+    std::vector<int> codes(n_proofs, NZCP_OK);
+    std::vector<std::string> msgs(n_provers);
+    std::vector<std::thread> threads;
+    for (int j = 0; j < n_provers; j++) {
+      threads.emplace_back([&, j] {
+        for (size_t i = j; i < n_proofs; i += n_provers) {
+          int rc = nzcp_prove(mine[j], wtns[i], wtns_len[i], r ? r + 32 * i : nullptr, s ? s + 32 * i : nullptr, &proofs[i],
+                              nullptr);
+          codes[i] = rc;
+          if (rc != NZCP_OK && msgs[j].empty()) msgs[j] = "proof " + std::to_string(i) + ": " + nzcp_last_error();
+        }
+      });
+    }
+    for (auto& t : threads) t.join();
+    if (status) for (size_t i = 0; i < n_proofs; i++) status[i] = codes[i];
+    for (size_t i = 0; i < n_proofs; i++)
+      if (codes[i] != NZCP_OK) {
+        std::string m;
+        for (auto& x : msgs) if (!x.empty()) { m = x; break; }
+        throw ApiError(codes[i], m);
+      }
+  });
+}
 
 }  // extern "C"

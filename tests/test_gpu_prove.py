@@ -246,3 +246,25 @@ def test_prover_pool_matches_single_prover(lib):
     out = groth16.prove({"type": "mem", "data": zb}, {"type": "mem", "data": wl[0]}, r=11, s=13)
     assert groth16.verify(vk, out["publicSignals"], out["proof"])
     groth16.terminate()
+
+
+def test_prove_batch_c_abi(lib):
+    """nzcp_prove_batch (library-side thread pool) == one nzcp_prove per witness; per-proof r, s; errors are reported."""
+    sc = api.SynthCircuit(seed=6, n_constraints=2000, n_public=7, n_free=50)
+    zb = sc.zkey([TOXIC[k] for k in ("tau", "alpha", "beta", "gamma", "delta")])
+    wl = [sc.wtns(200 + k) for k in range(8)]
+    rs = [(17 + k, 29 + 3 * k) for k in range(8)]
+    with api.Zkey(zb) as zk:
+        with api.Prover(zk) as pr:
+            single = [pr.prove(w, r=r, s=s)["proof"] for w, (r, s) in zip(wl, rs)]
+        for n_prov in (1, 3):
+            assert zk.prove_batch(wl, [r for r, _ in rs], [s for _, s in rs], n_provers=n_prov) == single
+        assert zk.prove_batch([], None, None) == []
+        rnd = zk.prove_batch(wl[:2])                       # random blinding
+        assert rnd[0] != single[0] and len(rnd[0]) == 256
+        bad = list(wl)
+        bad[5] = formats.write_wtns(formats.read_wtns(bytes(wl[5]))["witness"][:-1])
+        with pytest.raises(NzcpError, match="proof 5: Invalid witness length") as e:
+            zk.prove_batch(bad, [r for r, _ in rs], [s for _, s in rs])
+        assert e.value.code == -5
+        assert zk.prove_batch(wl, [r for r, _ in rs], [s for _, s in rs]) == single     # pool still healthy
