@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--batch", type=int, default=12, help="proofs per step per GPU")
     ap.add_argument("--shape", default="live", choices=sorted(SHAPES))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--provers", type=int, default=3, help="concurrent provers (host threads + stream sets) per GPU")
+    ap.add_argument("--provers", type=int, default=4, help="concurrent provers (host threads + stream sets) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -320,7 +320,7 @@ def roofline_block(dbg, zk, hbm, peak_src):
             "achieved": ach / 1e9, "peak": peak_mul / 1e9, "unit": "GFqmul/s", "frac": ach / peak_mul,
             "traffic": 2.31e9 * ent / 16776933.0,
             "launch_ms": acc_ms, "algorithmic_fq_mul": ent * 10,
-            "traffic_note": "ncu --set full (profiles/r01_ncu_accumulate_full.md): dram read+write 2.31 GB per launch vs "
+            "traffic_note": "ncu --set full (profiles/r01_ncu_accumulate_ntt_full.md): dram read+write 2.31 GB per launch vs "
                             "1.14 GB algorithmic (68 B/entry): 64-B points fetched as 128-B lines; DRAM at 10 % of peak, "
                             "fmaheavy (IMAD.WIDE) pipe 88 % active -- the kernel sits on the multiplier, not on memory",
             "peak_source": "measured here: %.2f T IMAD.WIDE.U32/s (32 per SM per clock, half the 32-bit IMAD rate) / 128 "

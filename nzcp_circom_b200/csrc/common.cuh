@@ -120,7 +120,6 @@ struct MsmRun {
   int n_digits = 0;           // base-32 digits of a bucket id
   uint32_t* heavy_list = nullptr;
   uint32_t* heavy_count = nullptr;   // [0] heavy buckets, [1] heavy chunks
-  uint32_t* chunk_cnt = nullptr;
   uint32_t* chunk_off = nullptr;
   void* chunk_partial = nullptr;
   void* out = nullptr;        // device: S_0 .. S_{n_digits-1}, T

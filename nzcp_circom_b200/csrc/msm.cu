@@ -707,7 +707,6 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
   r->marg = dev_alloc<unsigned char>(kMaxDigits * 32 * psz, &tot);
   r->heavy_list = dev_alloc<uint32_t>(sort->n_buckets, &tot);
   r->heavy_count = dev_alloc<uint32_t>(2, &tot);
-  r->chunk_cnt = dev_alloc<uint32_t>(sort->n_buckets + 1, &tot);
   r->chunk_off = dev_alloc<uint32_t>(sort->n_buckets + 1, &tot);
   r->chunk_partial = dev_alloc<unsigned char>((sort->max_tasks / kHeavyChunk + sort->n_buckets + 1) * psz, &tot);
   r->out = dev_alloc<unsigned char>((kMaxDigits + 1) * psz, &tot);
@@ -725,7 +724,6 @@ void msm_run_destroy(MsmRun* r) {
   cudaFree(r->marg);
   cudaFree(r->heavy_list);
   cudaFree(r->heavy_count);
-  cudaFree(r->chunk_cnt);
   cudaFree(r->chunk_off);
   cudaFree(r->chunk_partial);
   cudaFree(r->out);

@@ -21,6 +21,9 @@
 namespace nzcp {
 
 static constexpr int kNttThreads = 256;
+#ifndef NZCP_NTT_MIN_BLOCKS
+#define NZCP_NTT_MIN_BLOCKS 2
+#endif
 static constexpr int kMaxPassBits = 10;
 
 __device__ __forceinline__ uint32_t pad_idx(uint32_t l) { return l + (l >> 5); }
@@ -80,10 +83,89 @@ __device__ __forceinline__ void tile_stage(uint32_t* sm, uint32_t plane, uint32_
   }
 }
 
+// Two radix-2 stages (sl and sl + 1) at once on four elements held in registers: half the shared-memory traffic and
+// half the barriers of two tile_stage calls, same four twiddle products.  Elements l00, l01 (bit lb), l10, l11 (bit
+// lb+1).  w1 = twiddle of stage s for this group; w2, w3 = twiddles of stage s+1 for the l00/l10 and l01/l11 pairs
+// (w3 = w2 * w^(n/4)).
+template <bool DIT>
+__device__ __forceinline__ void tile_stage4(uint32_t* sm, uint32_t plane, uint32_t tile_elems, const Fr* tw, int log_n,
+                                            int lo, int sl, int cb, uint32_t low_bits) {
+  const int lb = sl + cb;
+  const int s = lo + sl;
+  const uint32_t cmask = (1u << cb) - 1;
+  for (uint32_t g = threadIdx.x; g < (tile_elems >> 2); g += blockDim.x) {
+    const uint32_t l00 = ((g >> lb) << (lb + 2)) | (g & ((1u << lb) - 1));
+    const uint32_t l01 = l00 | (1u << lb), l10 = l00 | (2u << lb), l11 = l00 | (3u << lb);
+    const uint32_t t = l00 >> cb;
+    const uint32_t imod = ((t & ((1u << sl) - 1)) << lo) | low_bits | (l00 & cmask);  // global index mod 2^s
+    const uint32_t e1 = imod << (log_n - 1 - s);
+    const uint32_t e2 = imod << (log_n - 2 - s);
+    const uint32_t e3 = e2 + (1u << (log_n - 2));
+    Fr x0 = sm_load(sm, plane, l00), x1 = sm_load(sm, plane, l01);
+    Fr x2 = sm_load(sm, plane, l10), x3 = sm_load(sm, plane, l11);
+    if (DIT) {
+      if (e1) {
+        Fr w1 = g_load(tw + e1);
+        x1 = fp_mul(x1, w1);
+        x3 = fp_mul(x3, w1);
+      }
+      Fr s0 = fp_add(x0, x1), s1 = fp_sub(x0, x1), s2 = fp_add(x2, x3), s3 = fp_sub(x2, x3);
+      if (e2) s2 = fp_mul(s2, g_load(tw + e2));
+      s3 = fp_mul(s3, g_load(tw + e3));
+      sm_store(sm, plane, l00, fp_add(s0, s2));
+      sm_store(sm, plane, l10, fp_sub(s0, s2));
+      sm_store(sm, plane, l01, fp_add(s1, s3));
+      sm_store(sm, plane, l11, fp_sub(s1, s3));
+    } else {
+      Fr p0 = fp_add(x0, x2), p2 = fp_sub(x0, x2), p1 = fp_add(x1, x3), p3 = fp_sub(x1, x3);
+      if (e2) p2 = fp_mul(p2, g_load(tw + e2));
+      p3 = fp_mul(p3, g_load(tw + e3));
+      Fr d0 = fp_sub(p0, p1), d1 = fp_sub(p2, p3);
+      if (e1) {
+        Fr w1 = g_load(tw + e1);
+        d0 = fp_mul(d0, w1);
+        d1 = fp_mul(d1, w1);
+      }
+      sm_store(sm, plane, l00, fp_add(p0, p1));
+      sm_store(sm, plane, l01, d0);
+      sm_store(sm, plane, l10, fp_add(p2, p3));
+      sm_store(sm, plane, l11, d1);
+    }
+  }
+}
+
+// All ns stages of a pass on the shared tile, two at a time (one radix-2 stage left over when ns is odd).
+template <bool DIT>
+__device__ __forceinline__ void tile_stages(uint32_t* sm, uint32_t plane, uint32_t tile_elems, const Fr* tw, int log_n,
+                                            int lo, int ns, int cb, uint32_t low_bits) {
+  if (DIT) {
+    int sl = 0;
+    for (; sl + 1 < ns; sl += 2) {
+      tile_stage4<true>(sm, plane, tile_elems, tw, log_n, lo, sl, cb, low_bits);
+      __syncthreads();
+    }
+    if (sl < ns) {
+      tile_stage<true>(sm, plane, tile_elems, tw, log_n, lo, sl, cb, low_bits);
+      __syncthreads();
+    }
+  } else {
+    int sl = ns - 1;
+    if (ns & 1) {
+      tile_stage<false>(sm, plane, tile_elems, tw, log_n, lo, sl, cb, low_bits);
+      __syncthreads();
+      sl--;
+    }
+    for (; sl >= 1; sl -= 2) {
+      tile_stage4<false>(sm, plane, tile_elems, tw, log_n, lo, sl - 1, cb, low_bits);
+      __syncthreads();
+    }
+  }
+}
+
 // Generic pass over global bits [lo, lo+ns).  Tile = 2^ns "rows" x 2^cb adjacent columns (cb <= lo).
 // grid.x = n >> (ns + cb) tiles, grid.y = batch.
 template <bool DIT>
-__global__ void __launch_bounds__(kNttThreads)
+__global__ void __launch_bounds__(kNttThreads, NZCP_NTT_MIN_BLOCKS)
 ntt_pass_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw, int log_n, int lo, int ns, int cb) {
   extern __shared__ uint32_t sm[];
   const uint32_t tile_elems = 1u << (ns + cb);
@@ -101,17 +183,7 @@ ntt_pass_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw, int log_n, int
     sm_store(sm, plane, l, g_load(x + gi));
   }
   __syncthreads();
-  if (DIT) {
-    for (int sl = 0; sl < ns; sl++) {
-      tile_stage<true>(sm, plane, tile_elems, tw, log_n, lo, sl, cb, low_bits);
-      __syncthreads();
-    }
-  } else {
-    for (int sl = ns - 1; sl >= 0; sl--) {
-      tile_stage<false>(sm, plane, tile_elems, tw, log_n, lo, sl, cb, low_bits);
-      __syncthreads();
-    }
-  }
+  tile_stages<DIT>(sm, plane, tile_elems, tw, log_n, lo, ns, cb, low_bits);
   for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) {
     uint32_t gi = base | ((l >> cb) << lo) | (l & cmask);
     g_store(x + gi, sm_load(sm, plane, l));
@@ -120,7 +192,7 @@ ntt_pass_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw, int log_n, int
 
 // Low pass of the pipeline: DIF stages ns-1..0 (inverse twiddles), scale by n^-1 * inc^bitrev(p), DIT stages
 // 0..ns-1 (forward twiddles).  Contiguous tile of 2^ns elements.
-__global__ void __launch_bounds__(kNttThreads)
+__global__ void __launch_bounds__(kNttThreads, NZCP_NTT_MIN_BLOCKS)
 ntt_fused_lo_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw_inv, const Fr* __restrict__ tw_fwd,
                     const Fr* __restrict__ scale, int log_n, int ns) {
   extern __shared__ uint32_t sm[];
@@ -130,19 +202,13 @@ ntt_fused_lo_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw_inv, const 
   const uint32_t base = blockIdx.x << ns;
   for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) sm_store(sm, plane, l, g_load(x + base + l));
   __syncthreads();
-  for (int sl = ns - 1; sl >= 0; sl--) {
-    tile_stage<false>(sm, plane, tile_elems, tw_inv, log_n, 0, sl, 0, 0);
-    __syncthreads();
-  }
+  tile_stages<false>(sm, plane, tile_elems, tw_inv, log_n, 0, ns, 0, 0);
   for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) {
     Fr v = sm_load(sm, plane, l);
     sm_store(sm, plane, l, fp_mul(v, g_load(scale + base + l)));
   }
   __syncthreads();
-  for (int sl = 0; sl < ns; sl++) {
-    tile_stage<true>(sm, plane, tile_elems, tw_fwd, log_n, 0, sl, 0, 0);
-    __syncthreads();
-  }
+  tile_stages<true>(sm, plane, tile_elems, tw_fwd, log_n, 0, ns, 0, 0);
   for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) g_store(x + base + l, sm_load(sm, plane, l));
 }
 
