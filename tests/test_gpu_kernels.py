@@ -153,12 +153,28 @@ def test_msm_edge_cases(lib, fixed_bases, g2):
     _msm_case(g2, [None] * 10, [rng.randrange(R) for _ in range(10)])
 
 
-@pytest.mark.parametrize("c", [2, 5, 9, 13, 16])
+@pytest.mark.parametrize("c", [2, 5, 9, 13, 16, 17, 19])   # <= 16: shared-memory histogram; above: global atomics
 def test_msm_window_sizes(lib, fixed_bases, c):
     rng = random.Random(c)
     pts = _rand_points(None, fixed_bases[0], rng, 200)
     scalars = [rng.randrange(R) for _ in range(190)] + [R - 1] * 10
     _msm_case(False, pts, scalars, window_bits=c)
+
+
+def test_msm_default_window_mid_size(lib):
+    """2^13 points with the default window (c = 10) and witness-like scalars: heavy bucket "1", adaptive task length,
+    two-stage heavy combine -- against the C oracle (the Python one is too slow here)."""
+    from oracle import cref
+    n = 1 << 13
+    bases = bytes(api.synth_points(9, n))
+    rng = random.Random(12)
+    sc = [rng.choice([0, 1, 1, 1, rng.randrange(256), rng.randrange(R)]) for _ in range(n)]
+    scb = b"".join(le32(x) for x in sc)
+    got, _ = api.msm(bases, scb, n)
+    assert got == cref.msm(bases, scb, n, False, 4)
+    b2 = bytes(api.synth_points(10, 2048, g2=True))
+    got2, _ = api.msm(b2, scb[:2048 * 32], 2048, g2=True)
+    assert got2 == cref.msm(b2, scb[:2048 * 32], 2048, True, 4)
 
 
 def test_msm_rejects_non_canonical_scalar(lib, fixed_bases):
