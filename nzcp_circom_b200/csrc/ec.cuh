@@ -186,13 +186,22 @@ HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
   acc.zzz = f_mul(f_mul(acc.zzz, b.zzz), ppp);
 }
 
-// k * p, k = plain 256-bit little-endian scalar (8 limbs); left-to-right double-and-add.
+// k * p, k = plain 256-bit little-endian scalar (8 limbs); left-to-right with a 4-bit window (table of 1..15 times p).
 template <class F>
 HDN inline XYZZ<F> xyzz_mul(const XYZZ<F>& p, const uint32_t* k) {
+  XYZZ<F> tab[16];
+  tab[0] = XYZZ<F>::inf();
+  tab[1] = p;
+  for (int i = 2; i < 16; i++) {
+    tab[i] = tab[i - 1];
+    xyzz_add(tab[i], p);
+  }
   XYZZ<F> r = XYZZ<F>::inf();
-  for (int i = 255; i >= 0; i--) {
-    r = xyzz_dbl(r);
-    if ((k[i >> 5] >> (i & 31)) & 1) xyzz_add(r, p);
+  for (int i = 63; i >= 0; i--) {
+    if (!r.is_inf())
+      for (int d = 0; d < 4; d++) r = xyzz_dbl(r);
+    uint32_t nib = (k[i >> 3] >> ((i & 7) * 4)) & 15;
+    if (nib) xyzz_add(r, tab[nib]);
   }
   return r;
 }

@@ -402,6 +402,69 @@ __device__ __forceinline__ Fp<P> fp_mul_ptx(const Fp<P>& a, const Fp<P>& b) {
 }
 #endif  // __CUDA_ARCH__
 
+// ------------------------------------------------------------------------------------------ host 64-bit core
+// The O(1) host glue (proof finalisation: two 256-bit scalar multiplications and three affine conversions per proof)
+// sits on the per-proof latency path; on the CPU the same CIOS product runs ~3x faster on 4 x 64-bit digits.
+#if !defined(__CUDA_ARCH__)
+template <class P>
+inline Fp<P> fp_mul_host64(const Fp<P>& a, const Fp<P>& b) {
+  typedef unsigned __int128 u128;
+  uint64_t A[4], B[4], M[4];
+  for (int i = 0; i < 4; i++) {
+    A[i] = a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+    B[i] = b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+    M[i] = P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+  }
+  // -p^-1 mod 2^64 from the 32-bit constant by one Newton step: x' = x * (2 + p * x)  (x = -p^-1)
+  uint64_t inv = (uint64_t)P::INV;
+  inv = inv * (2 + M[0] * inv);
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)A[j] * B[i] + t[j];
+      t[j] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (uint64_t)c;
+    t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * inv;
+    c = ((u128)m * M[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * M[j] + t[j];
+      t[j - 1] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (uint64_t)c;
+    t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  bool ge = t[4] != 0;
+  if (!ge) {
+    ge = true;
+    for (int i = 3; i >= 0; i--) {
+      if (t[i] > M[i]) break;
+      if (t[i] < M[i]) { ge = false; break; }
+    }
+  }
+  if (ge) {
+    uint64_t bw = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)t[i] - M[i] - bw;
+      t[i] = (uint64_t)d;
+      bw = (uint64_t)(d >> 64) & 1;
+    }
+  }
+  Fp<P> r;
+  for (int i = 0; i < 4; i++) {
+    r.v[2 * i] = (uint32_t)t[i];
+    r.v[2 * i + 1] = (uint32_t)(t[i] >> 32);
+  }
+  return r;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------ public ops
 template <class P>
 HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
@@ -423,8 +486,10 @@ template <class P>
 HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #if defined(__CUDA_ARCH__) && NZCP_MUL_PTX
   return fp_mul_ptx(a, b);
-#else
+#elif defined(__CUDA_ARCH__)
   return fp_mul_portable(a, b);
+#else
+  return fp_mul_host64(a, b);
 #endif
 }
 template <class P>

@@ -35,7 +35,10 @@ namespace nzcp {
 
 static constexpr int kTaskLenMax = 64;     // entries per accumulate task: 8..64, picked on the device from the entry
 static constexpr int kTaskLenMin = 8;      //   count so that the tasks about fill the GPU once (flags[4])
-static constexpr int kTargetTasks = 148 * 640;  // resident accumulate threads of a B200 (G1: 5 blocks of 128 per SM)
+#ifndef NZCP_TARGET_TASKS
+#define NZCP_TARGET_TASKS (148 * 640)
+#endif
+static constexpr int kTargetTasks = NZCP_TARGET_TASKS;  // resident accumulate threads of a B200 (G1: 5 blocks of 128 per SM)
 static constexpr int kHeavyTasks = 16;     // buckets with more tasks than this go to the block-wide combine
 static constexpr int kHeavyThreads = 128;
 static constexpr int kHeavyChunk = 512;     // task partials per stage-1 block of the heavy combine

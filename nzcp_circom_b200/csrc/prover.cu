@@ -319,6 +319,13 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
   msm_run_launch(&p->run_h, &p->sort_h, &zk->tab_h, sm);
   NZCP_CUDA(cudaEventRecord(p->ev[4], sm));
   if (dbg && dbg->h_scalars) NZCP_CUDA(cudaMemcpyAsync(dbg->h_scalars, p->d_h, n * sizeof(Fr), cudaMemcpyDeviceToHost, sm));
+  // While the GPU works: the blinding terms that depend only on r, s and the key (r*delta1, s*delta1, s*delta2,
+  // -rs*delta1) -- four of the six scalar multiplications of the final combination leave the latency path.
+  const Fr r = fp_from_bytes_plain<FrParams>(rb), s = fp_from_bytes_plain<FrParams>(sb);
+  const Fr neg_rs = fp_neg(fp_from_mont(fp_mul(fp_to_mont(r), fp_to_mont(s))));
+  const G1XYZZ d1 = G1XYZZ::from_affine(zk->delta1);
+  const G1XYZZ r_d1 = xyzz_mul(d1, r.v), s_d1 = xyzz_mul(d1, s.v), nrs_d1 = xyzz_mul(d1, neg_rs.v);
+  const G2XYZZ s_d2 = xyzz_mul(G2XYZZ::from_affine(zk->delta2), s.v);
   for (int k = 0; k < 4; k++) NZCP_CUDA(cudaStreamSynchronize(p->st_msm[k]));
   NZCP_CUDA(cudaStreamSynchronize(sm));
 
@@ -364,25 +371,20 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
     dbg->total_ms = el(0, 4);
   }
   // finalisation (tail of groth16Prove): O(1) group operations on the host, as snarkjs does on its main thread
-  Fr r = fp_from_bytes_plain<FrParams>(rb), s = fp_from_bytes_plain<FrParams>(sb);
-  Fr rs = fp_from_mont(fp_mul(fp_to_mont(r), fp_to_mont(s)));
-  Fr neg_rs = fp_neg(rs);
-  G1XYZZ d1 = G1XYZZ::from_affine(zk->delta1);
-  G2XYZZ d2 = G2XYZZ::from_affine(zk->delta2);
   G1XYZZ pi_a = A;
   xyzz_add(pi_a, G1XYZZ::from_affine(zk->alpha1));
-  xyzz_add(pi_a, xyzz_mul(d1, r.v));
+  xyzz_add(pi_a, r_d1);
   G2XYZZ pi_b = B2;
   xyzz_add(pi_b, G2XYZZ::from_affine(zk->beta2));
-  xyzz_add(pi_b, xyzz_mul(d2, s.v));
+  xyzz_add(pi_b, s_d2);
   G1XYZZ pib1 = B1;
   xyzz_add(pib1, G1XYZZ::from_affine(zk->beta1));
-  xyzz_add(pib1, xyzz_mul(d1, s.v));
+  xyzz_add(pib1, s_d1);
   G1XYZZ pi_c = C;
   xyzz_add(pi_c, H);
   xyzz_add(pi_c, xyzz_mul(pi_a, s.v));
   xyzz_add(pi_c, xyzz_mul(pib1, r.v));
-  xyzz_add(pi_c, xyzz_mul(d1, neg_rs.v));
+  xyzz_add(pi_c, nrs_d1);
   g1_to_plain_bytes(pi_a, proof->pi_a);
   g2_to_plain_bytes(pi_b, proof->pi_b);
   g1_to_plain_bytes(pi_c, proof->pi_c);
