@@ -36,26 +36,30 @@ HD Fq2 f_add(const Fq2& a, const Fq2& b) { return Fq2{fp_add(a.c0, b.c0), fp_add
 HD Fq2 f_sub(const Fq2& a, const Fq2& b) { return Fq2{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
 HD Fq2 f_neg(const Fq2& a) { return Fq2{fp_neg(a.c0), fp_neg(a.c1)}; }
 HD Fq2 f_dbl(const Fq2& a) { return Fq2{fp_add(a.c0, a.c0), fp_add(a.c1, a.c1)}; }
-// On the device the Fq product inside Fq2 arithmetic is a real function call: a G2 mixed addition is 28 Fq products,
-// and inlining all of them (~6 000 SASS instructions) made the G2 bucket-accumulate kernel stall on instruction fetch
-// (ncu: stalled_no_instruction ~3 per issue).  One shared ~200-instruction body stays resident in the i-cache.
-#if defined(__CUDA_ARCH__) && !defined(NZCP_FQ2_INLINE)
-__device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return fp_mul(a, b); }
-#define NZCP_FQ2_MUL(a, b) fq_mul_call(a, b)
-#else
-#define NZCP_FQ2_MUL(a, b) fp_mul(a, b)
-#endif
-HD Fq2 f_mul(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 Fq mul; u^2 = -1
-  Fq t0 = NZCP_FQ2_MUL(a.c0, b.c0);
-  Fq t1 = NZCP_FQ2_MUL(a.c1, b.c1);
-  Fq t2 = NZCP_FQ2_MUL(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+// On the device an Fq2 product / square is a real function call: a G2 mixed addition is 28 Fq products, and inlining
+// all of them (~6 000 SASS instructions) made the G2 bucket-accumulate kernel stall on instruction fetch (ncu:
+// stalled_no_instruction ~3 per issue).  Two shared bodies (3 and 2 Fq products) stay resident in the i-cache; calling
+// at Fq2 granularity moves 48 registers per 3 products instead of 24 per product.
+HD Fq2 f2_mul_inline(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 Fq mul; u^2 = -1
+  Fq t0 = fp_mul(a.c0, b.c0);
+  Fq t1 = fp_mul(a.c1, b.c1);
+  Fq t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
   return Fq2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
 }
-HD Fq2 f_sqr(const Fq2& a) {  // (c0+c1)(c0-c1) + 2 c0 c1 u : 2 Fq mul
-  Fq t0 = NZCP_FQ2_MUL(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
-  Fq t1 = NZCP_FQ2_MUL(a.c0, a.c1);
+HD Fq2 f2_sqr_inline(const Fq2& a) {  // (c0+c1)(c0-c1) + 2 c0 c1 u : 2 Fq mul
+  Fq t0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
+  Fq t1 = fp_mul(a.c0, a.c1);
   return Fq2{t0, fp_add(t1, t1)};
 }
+#if defined(__CUDA_ARCH__) && !defined(NZCP_FQ2_INLINE)
+__device__ __noinline__ Fq2 f2_mul_call(Fq2 a, Fq2 b) { return f2_mul_inline(a, b); }
+__device__ __noinline__ Fq2 f2_sqr_call(Fq2 a) { return f2_sqr_inline(a); }
+HD Fq2 f_mul(const Fq2& a, const Fq2& b) { return f2_mul_call(a, b); }
+HD Fq2 f_sqr(const Fq2& a) { return f2_sqr_call(a); }
+#else
+HD Fq2 f_mul(const Fq2& a, const Fq2& b) { return f2_mul_inline(a, b); }
+HD Fq2 f_sqr(const Fq2& a) { return f2_sqr_inline(a); }
+#endif
 HDN inline Fq2 f_inv(const Fq2& a) {
   Fq d = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
   return Fq2{fp_mul(a.c0, d), fp_neg(fp_mul(a.c1, d))};
