@@ -611,13 +611,9 @@ void msm_sort_create(MsmSort* s, size_t n_points, int c) {
   s->cursors = dev_alloc<uint32_t>(n_ctr + 1, &tot);
   s->bcount = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
   s->block_sums = dev_alloc<uint32_t>(2 * (n_ctr / kScanBlock + 2), &tot);
-  if (s->smem_hist) {
-    static bool attr = false;
-    if (!attr) {
-      NZCP_CUDA(cudaFuncSetAttribute(msm_digits_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHistBuckets * 4));
-      NZCP_CUDA(cudaFuncSetAttribute(msm_digits_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHistBuckets * 4));
-      attr = true;
-    }
+  if (s->smem_hist) {  // function attributes are per device: set them whenever a plan is created on the current one
+    NZCP_CUDA(cudaFuncSetAttribute(msm_digits_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHistBuckets * 4));
+    NZCP_CUDA(cudaFuncSetAttribute(msm_digits_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHistBuckets * 4));
   }
   s->entries = dev_alloc<uint32_t>(max_entries, &tot);
   s->task_off = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
@@ -705,6 +701,14 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
   r->g2 = g2;
   size_t psz = g2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
   size_t tot = 0;
+  if (g2) {  // > 48 KB of dynamic shared memory; function attributes are per device
+    NZCP_CUDA(cudaFuncSetAttribute(msm_combine_heavy_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kHeavyThreads * sizeof(G2XYZZ))));
+    NZCP_CUDA(cudaFuncSetAttribute(msm_combine_heavy2_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kHeavyThreads * sizeof(G2XYZZ))));
+    NZCP_CUDA(cudaFuncSetAttribute(msm_marginal_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kMargThreads * sizeof(G2XYZZ))));
+  }
   r->partial = dev_alloc<unsigned char>(sort->max_tasks * psz, &tot);
   r->buckets = dev_alloc<unsigned char>(sort->n_buckets * psz, &tot);
   r->marg = dev_alloc<unsigned char>(kMaxDigits * 32 * psz, &tot);
@@ -773,16 +777,6 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
 }
 
 void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    NZCP_CUDA(cudaFuncSetAttribute(msm_combine_heavy_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kHeavyThreads * sizeof(G2XYZZ))));
-    NZCP_CUDA(cudaFuncSetAttribute(msm_combine_heavy2_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kHeavyThreads * sizeof(G2XYZZ))));
-    NZCP_CUDA(cudaFuncSetAttribute(msm_marginal_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kMargThreads * sizeof(G2XYZZ))));
-    attr_done = true;
-  }
   if (r->g2 != table->g2) throw std::runtime_error("msm: run and table group mismatch");
   if (r->g2)
     msm_run_launch_t<Fq2>(r, sort, table, st);

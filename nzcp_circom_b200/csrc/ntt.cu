@@ -263,18 +263,17 @@ static size_t pass_smem_bytes(int ns, int cb) {
   return 8 * (tile + (tile >> 5) + 1) * sizeof(uint32_t);
 }
 
+// Function attributes are per device: called from ntt_domain_create, i.e. once per domain per device.
 static void ensure_smem_attrs() {
-  static bool done = false;
-  if (done) return;
   int mx = (int)pass_smem_bytes(kMaxPassBits, 1);
   NZCP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   NZCP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   NZCP_CUDA(cudaFuncSetAttribute(ntt_fused_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  done = true;
 }
 
 void ntt_domain_create(NttDomain* d, int log_n, cudaStream_t st) {
   if (log_n < 1 || log_n > 27) throw std::runtime_error("ntt: unsupported domain size");
+  ensure_smem_attrs();
   d->log_n = log_n;
   size_t n = (size_t)1 << log_n;
   std::vector<Fr> fwd(n / 2), inv(n / 2), scale(n);
@@ -339,7 +338,6 @@ static void launch_pass(Fr* data, const Fr* tw, int log_n, int lo, int ns, int b
 }
 
 void ntt_coset_pipeline(const NttDomain& d, Fr* data, int batch, cudaStream_t st) {
-  ensure_smem_attrs();
   int lo_bits = d.log_n < kMaxPassBits ? d.log_n : kMaxPassBits;
   auto hp = hi_passes(d.log_n, lo_bits);
   for (int i = (int)hp.size() - 1; i >= 0; i--)
@@ -352,7 +350,6 @@ void ntt_coset_pipeline(const NttDomain& d, Fr* data, int batch, cudaStream_t st
 }
 
 static void ntt_natural(const NttDomain& d, Fr* data, Fr* tmp, const Fr* tw, cudaStream_t st) {
-  ensure_smem_attrs();
   size_t n = (size_t)1 << d.log_n;
   bitrev_permute_kernel<<<div_up(n, 256), 256, 0, st>>>(data, tmp, d.log_n);
   NZCP_LAUNCH_CHECK();

@@ -268,3 +268,18 @@ def test_prove_batch_c_abi(lib):
             zk.prove_batch(bad, [r for r, _ in rs], [s for _, s in rs])
         assert e.value.code == -5
         assert zk.prove_batch(wl, [r for r, _ in rs], [s for _, s in rs]) == single     # pool still healthy
+
+
+def test_two_devices_in_one_process(lib):
+    """The C ABI takes a device index: keys on two GPUs of one process give the same proofs (kernel attributes such as
+    the > 48 KB shared-memory opt-in are per device)."""
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c = tiny_case(41, 700, 5, 16)
+    outs = []
+    for dev in (0, 1):
+        with api.Zkey(c["zkey_bytes"], device=dev) as zk, api.Prover(zk) as pr:
+            outs.append(pr.prove(c["wtns_bytes"], r=9, s=10, debug=True, want_h=True))
+    assert outs[0]["proof"] == outs[1]["proof"] and outs[0]["h"] == outs[1]["h"]
+    exp, _ = oprover.prove(formats.read_zkey(c["zkey_bytes"]), c["witness"], 9, 10)
+    assert outs[1]["proof"] == oprover.proof_to_bytes(exp)
