@@ -331,7 +331,11 @@ static std::vector<std::pair<int, int>> hi_passes(int log_n, int lo_bits) {
 
 template <bool DIT>
 static void launch_pass(Fr* data, const Fr* tw, int log_n, int lo, int ns, int batch, cudaStream_t st) {
-  int cb = lo >= 1 ? 1 : 0;
+  // adjacent columns per tile row: as many as keep the tile at 2^(kMaxPassBits+1) elements, so short passes (the split
+  // of 11..19 high bits at 2^21..2^24) still fill the block and read 2^cb * 32 contiguous bytes per row
+  int cb = kMaxPassBits + 1 - ns;
+  if (cb > lo) cb = lo;
+  if (cb < 0) cb = 0;
   dim3 grid(1u << (log_n - ns - cb), batch);
   ntt_pass_kernel<DIT><<<grid, kNttThreads, pass_smem_bytes(ns, cb), st>>>(data, tw, log_n, lo, ns, cb);
   NZCP_LAUNCH_CHECK();
