@@ -7,6 +7,22 @@
  * the `.zkey` / `.wtns` files ignored at /root/reference/.gitignore:2-4.  A Node N-API addon (or Python ctypes,
  * see INTEGRATION.md) binds these entry points 1:1.
  *
+ * What each entry point replaces.  The reference has NO call site for the prover (its tests stop at
+ * `cir.calculateWitness(input, true)`, /root/reference/test/nzcp.js:39, and read the public signals as witness[1..513],
+ * test/nzcp.js:41-48); the interface replaced is that of the pinned, un-vendored packages, cited here by the lock-file
+ * line that pins each one:
+ *   nzcp_zkey_load      binfileutils readBinFile + snarkjs zkey_utils.js readHeader + the readSection(4..9) calls of
+ *                       groth16_prove.js (yarn.lock:385-388 @iden3/binfileutils 0.0.10; yarn.lock:987-999 snarkjs 0.4.12)
+ *   nzcp_prove*         snarkjs groth16_prove.js groth16Prove(zkeyFileName, witnessFileName) incl. wtns_utils.js
+ *                       readHeader and the three error checks (yarn.lock:987-999)
+ *   nzcp_prove_batch    no snarkjs equivalent (one proof per call there); BASELINE.json configs[2] batch mode
+ *   nzcp_ntt[_coset]    ffjavascript engine_fft.js Fr.fft / Fr.ifft, engine_applykey.js batchApplyKey (yarn.lock:408-416)
+ *   nzcp_msm            ffjavascript engine_multiexp.js G1/G2.multiExpAffine (yarn.lock:408-416) over wasmcurves
+ *                       build_multiexp.js (yarn.lock:1132-1135)
+ *   nzcp_field_op       wasmcurves build_f1m.js f1m_mul / f1m_add / f1m_sub (yarn.lock:1132-1135)
+ *   nzcp_synth_*        snarkjs zkey_new.js with a known tau in place of the ptau file /root/reference/Makefile:31 names;
+ *                       shapes from circuits/nzcp_exampleTest.circom:4 and circuits/nzcp_liveTest.circom:4
+ *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative NZCP_E_* code and
  * never throws across the boundary; `nzcp_last_error()` returns a thread-local message for the last failure.
  * All field elements crossing the ABI are 32-byte little-endian integers.  A handle may be used by one thread at a
