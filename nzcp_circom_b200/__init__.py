@@ -7,6 +7,6 @@
 All proving work runs in libnzcp_prover.so (hand-written sm_100a CUDA behind the C ABI in include/nzcp_prover.h).
 There is no CPU fallback: importing works anywhere, proving raises NzcpError(NZCP_E_CUDA) without a GPU.
 """
-from . import groth16  # noqa: F401
+from . import groth16, nzcp_input  # noqa: F401
 from ._lib import NzcpError, load  # noqa: F401
 from .api import Prover, SynthCircuit, Zkey  # noqa: F401
