@@ -13,7 +13,7 @@
 // key).  With it  sum_i s_i P_i = sum_{i,w} d_{i,w} T[w][i]  is a single bucket problem: all windows share one set
 // of 2^(c-1) buckets, there is no per-window reduction and no Horner pass.  One MSM is a stream-ordered chain:
 //   sort (once per scalar vector, shared by A / B1 / B2 / C which all use the witness):
-//     1 digits/count   signed c-bit digits (c = 16 at 2^20), histogram over 2^15 buckets
+//     1 digits/count   signed c-bit digits (c = 16 at 2^20), histogram over 2^15 buckets in per-SM shared memory
 //     2 scan           exclusive prefix sum of the bucket counts
 //     3 scatter        (w * n + i) | sign << 31 written into the bucket's slot range
 //     4 tasks          every bucket is cut into tasks of <= 64 entries, so the 0/1-heavy witness distribution
@@ -33,13 +33,19 @@
 
 namespace nzcp {
 
-static constexpr int kTaskLenMax = 64;     // entries per accumulate task: 8..64, picked on the device from the entry
+#ifndef NZCP_TASK_LEN_MAX
+#define NZCP_TASK_LEN_MAX 64
+#endif
+static constexpr int kTaskLenMax = NZCP_TASK_LEN_MAX;  // entries per accumulate task: 8..64, picked on the device from the entry
 static constexpr int kTaskLenMin = 8;      //   count so that the tasks about fill the GPU once (flags[4])
 #ifndef NZCP_TARGET_TASKS
 #define NZCP_TARGET_TASKS (148 * 640)
 #endif
 static constexpr int kTargetTasks = NZCP_TARGET_TASKS;  // resident accumulate threads of a B200 (G1: 5 blocks of 128 per SM)
-static constexpr int kHeavyTasks = 16;     // buckets with more tasks than this go to the block-wide combine
+#ifndef NZCP_HEAVY_TASKS
+#define NZCP_HEAVY_TASKS 16
+#endif
+static constexpr int kHeavyTasks = NZCP_HEAVY_TASKS;  // buckets with more tasks than this go to the block-wide combine
 static constexpr int kHeavyThreads = 128;
 static constexpr int kHeavyChunk = 512;     // task partials per stage-1 block of the heavy combine
 static constexpr int kMaxDigits = 4;        // base-32 digits of a bucket id (c <= 20)
