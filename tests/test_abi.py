@@ -108,3 +108,24 @@ def test_zkey_format_errors_are_reported_before_touching_the_gpu(lib):
     with pytest.raises(NzcpError) as e:
         api.Zkey(z3)
     assert e.value.code == _lib.NZCP_E_CURVE
+
+
+def test_null_and_bad_arguments_return_error_codes(lib):
+    """Misuse never crashes the host: null pointers / bad sizes come back as NZCP_E_ARG (or FORMAT) with a message."""
+    import ctypes as C
+    p = C.c_void_p()
+    assert lib.nzcp_zkey_load(None, 0, 0, C.byref(p)) == _lib.NZCP_E_ARG
+    assert lib.nzcp_zkey_load(b"zkey", 4, 0, None) == _lib.NZCP_E_ARG
+    assert lib.nzcp_zkey_load(b"zkey\x01\x00\x00\x00", 8, 0, C.byref(p)) == _lib.NZCP_E_FORMAT
+    assert b"Invalid File format" in lib.nzcp_last_error() or b"truncated" in lib.nzcp_last_error()
+    assert lib.nzcp_prover_create(None, C.byref(p)) == _lib.NZCP_E_ARG
+    assert lib.nzcp_prove(None, b"", 0, None, None, None, None) == _lib.NZCP_E_ARG
+    assert lib.nzcp_prove_batch(None, None, None, 0, None, None, None, 0, None) == _lib.NZCP_E_ARG
+    assert lib.nzcp_zkey_info_get(None, None) == _lib.NZCP_E_ARG
+    assert lib.nzcp_ntt(None, 4, 0, 0, None) == _lib.NZCP_E_ARG
+    assert lib.nzcp_msm(None, None, 5, 0, 0, 0, None, None) == _lib.NZCP_E_ARG
+    assert lib.nzcp_host_root_of_unity(29, (C.c_uint8 * 32)()) == _lib.NZCP_E_ARG
+    assert lib.nzcp_synth_create(1, 0, 0, 0, C.byref(p)) == _lib.NZCP_E_ARG
+    lib.nzcp_zkey_free(None)          # no-ops
+    lib.nzcp_prover_free(None)
+    lib.nzcp_synth_free(None)
