@@ -264,6 +264,8 @@ def main():
     correct = None
     value = world * B * args.steps / (ms_dev / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
+    n_dig = lambda npts: ((16 if npts >= (1 << 19) else 14 if npts >= (1 << 17) else 12) - 1 + 4) // 5  # noqa: E731
+    d2h_per_proof = 3 * (n_dig(m) + 1) * 128 + (n_dig(m) + 1) * 256 + (n_dig(zk.domain_size) + 1) * 128 + 64
     if rank == 0:
         hbm, peak_src = peaks()
         line = {
@@ -276,7 +278,9 @@ def main():
                            l2="inputs exceed L2: each proof streams ~%.0f MB of proving key" % (zk.device_bytes / 1e6),
                            **dims),
             "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": B * m * 32,
-                    "d2h_bytes_per_step": B * 256, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": B * d2h_per_proof, "ms_per_step": ms_e2e / args.steps,
+                    "d2h_note": "per proof: 4 G1 + 1 G2 MSM results as (digits + 1) XYZZ points each + 2 x 32 B of sort flags; "
+                                "the 256-byte proof itself is assembled on the host"},
             "p50_latency_ms": 1e3 * statistics.median(lat) if lat else None,
             "gpu_launches": launches, "clocks": clocks, "stage_ms": dbg["stage_ms"],
         }
