@@ -450,7 +450,8 @@ template <class F>
 __global__ void __launch_bounds__(kHeavyThreads)
 msm_combine_heavy_kernel(const uint32_t* __restrict__ task_off, const XYZZ<F>* __restrict__ partial,
                          const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count,
-                         const uint32_t* __restrict__ chunk_off, XYZZ<F>* __restrict__ chunk_partial) {
+                         const uint32_t* __restrict__ chunk_off, XYZZ<F>* __restrict__ chunk_partial,
+                         XYZZ<F>* __restrict__ buckets) {
   extern __shared__ unsigned char heavy_sm_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_sm_raw);
   const uint32_t n_heavy = *heavy_count;
@@ -470,7 +471,10 @@ msm_combine_heavy_kernel(const uint32_t* __restrict__ task_off, const XYZZ<F>* _
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) xyzz_add(acc, partial[t0 + j]);
     acc = block_sum(acc, sm);
-    if (threadIdx.x == 0) chunk_partial[ch] = acc;
+    if (threadIdx.x == 0) {
+      if (chunk_off[lo + 1] - chunk_off[lo] == 1) buckets[b] = acc;   // one chunk: this is the bucket's sum
+      else chunk_partial[ch] = acc;
+    }
   }
 }
 
@@ -484,6 +488,7 @@ msm_combine_heavy2_kernel(const uint32_t* __restrict__ heavy_list, const uint32_
   const uint32_t n_heavy = *heavy_count;
   for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
     const uint32_t c0 = chunk_off[h], nc = chunk_off[h + 1] - c0;
+    if (nc <= 1) continue;                                             // stage 1 already wrote the bucket
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t j = threadIdx.x; j < nc; j += blockDim.x) xyzz_add(acc, chunk_partial[c0 + j]);
     acc = block_sum(acc, sm);
@@ -766,8 +771,11 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
   msm_heavy_scan_kernel<<<1, 1024, 0, st>>>(s->task_off, r->heavy_list, r->heavy_count, r->chunk_off);
   NZCP_LAUNCH_CHECK();
   XYZZ<F>* chunk_partial = reinterpret_cast<XYZZ<F>*>(r->chunk_partial);
-  msm_combine_heavy_kernel<F><<<296, kHeavyThreads, kHeavyThreads * psz, st>>>(s->task_off, partial, r->heavy_list,
-                                                                               r->heavy_count, r->chunk_off, chunk_partial);
+  // the chunk count is only known on the device: a grid large enough for "every bucket is heavy" (standalone MSMs of
+  // 2^22+ points), whose surplus blocks exit at once in the prover's case (a few hundred heavy buckets at most)
+  msm_combine_heavy_kernel<F><<<148 * 16, kHeavyThreads, kHeavyThreads * psz, st>>>(s->task_off, partial, r->heavy_list,
+                                                                                    r->heavy_count, r->chunk_off, chunk_partial,
+                                                                                    buckets);
   NZCP_LAUNCH_CHECK();
   msm_combine_heavy2_kernel<F><<<148, kHeavyThreads, kHeavyThreads * psz, st>>>(r->heavy_list, r->heavy_count, r->chunk_off,
                                                                                 chunk_partial, buckets);
