@@ -325,9 +325,12 @@ msm_task_fill_kernel(const uint32_t* __restrict__ bcount, const uint32_t* __rest
     uint32_t mid = (lo + hi) >> 1;
     if (task_off[mid] <= t) lo = mid; else hi = mid;
   }
-  const uint32_t done = (t - task_off[lo]) * tl;
-  const uint32_t left = bcount[lo] - done;
-  tasks[t] = make_uint2(offsets[lo * n_copies] + done, left < tl ? left : tl);
+  // balanced split: the bucket's k = ceil(count / tl) tasks get count / k entries each (+1 for the first count % k), so
+  // the lanes of a warp finish together instead of waiting for full-length neighbours of a short remainder task
+  (void)tl;
+  const uint32_t k = task_off[lo + 1] - task_off[lo], j = t - task_off[lo];
+  const uint32_t cnt = bcount[lo], base = cnt / k, rem = cnt % k;
+  tasks[t] = make_uint2(offsets[lo * n_copies] + j * base + (j < rem ? j : rem), base + (j < rem ? 1u : 0u));
 }
 
 // ------------------------------------------------------------------------------------------------ run
