@@ -400,6 +400,131 @@ __device__ __forceinline__ Fp<P> fp_mul_ptx(const Fp<P>& a, const Fp<P>& b) {
   for (int i = 0; i < 8; i++) r.v[i] = ev[i];
   return r;
 }
+
+// ---- wide product + separate reduction (used by the lazy-reduction Fq2 product in ec.cuh) -------------------------
+// T[0..15] = a * b as a full 512-bit integer: the same even/odd rows as fp_mul_ptx with the reduction rows left out;
+// after row i the low limb of the running value is product limb i.  a, b < 2^255.
+__device__ __forceinline__ void fp_mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+  uint32_t ev[8], od[8];
+  fp_mad_row<true>(ev, od, a, b[0]);
+  T[0] = ev[0];
+  fp_mad_row<false>(od, ev, a, b[1]);
+  T[1] = od[0];
+  fp_mad_row<false>(ev, od, a, b[2]);
+  T[2] = ev[0];
+  fp_mad_row<false>(od, ev, a, b[3]);
+  T[3] = od[0];
+  fp_mad_row<false>(ev, od, a, b[4]);
+  T[4] = ev[0];
+  fp_mad_row<false>(od, ev, a, b[5]);
+  T[5] = od[0];
+  fp_mad_row<false>(ev, od, a, b[6]);
+  T[6] = ev[0];
+  fp_mad_row<false>(od, ev, a, b[7]);
+  T[7] = od[0];
+  // high half = (even >> 32) + odd, even = od, odd = ev
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, 0;"
+      : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7])
+      : "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+#pragma unroll
+  for (int i = 0; i < 8; i++) T[8 + i] = ev[i];
+}
+
+// After a reduction row zeroed even[0]: divide the running value by 2^32.  `ev` = the old odd array (becomes the even
+// one), `od` = the old even array (rewritten as the new odd one): ev0 += od1, od[k] = od[k+2] + carry, top limbs 0.
+__device__ __forceinline__ void fp_shift_row(uint32_t* ev, uint32_t* od) {
+  asm("add.cc.u32 %0, %0, %2;\n\t"
+      "addc.cc.u32 %1, %3, 0;\n\t"
+      "addc.cc.u32 %2, %4, 0;\n\t"
+      "addc.cc.u32 %3, %5, 0;\n\t"
+      "addc.cc.u32 %4, %6, 0;\n\t"
+      "addc.cc.u32 %5, %7, 0;\n\t"
+      "addc.cc.u32 %6, %8, 0;\n\t"
+      "addc.u32 %7, 0, 0;\n\t"
+      "mov.u32 %8, 0;"
+      : "+r"(ev[0]), "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]));
+}
+
+// 8-limb add / subtract with carry (borrow) in and out as 0/1 values -- halves of the 16-limb operations below.
+__device__ __forceinline__ uint32_t fp_add8c(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t cin) {
+  uint32_t cout;
+  asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"   // carry flag := cin
+      "addc.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(cout)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+  return cout;
+}
+__device__ __forceinline__ uint32_t fp_sub8b(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t bin) {
+  uint32_t bout;
+  asm("sub.cc.u32 %8, 0, %25;\n\t"            // borrow flag := bin
+      "subc.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(bout)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(bin));
+  return bout & 1u;
+}
+__device__ __forceinline__ void fp_add16(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t c = fp_add8c(r, a, b, 0u);
+  fp_add8c(r + 8, a + 8, b + 8, c);
+}
+__device__ __forceinline__ void fp_sub16(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t bw = fp_sub8b(r, a, b, 0u);
+  fp_sub8b(r + 8, a + 8, b + 8, bw);
+}
+
+// r = T / 2^256 mod p (canonical) for a 16-limb T < p * 2^256: Montgomery-reduce the LOW half (eight reduction rows, the
+// running value never exceeds p + 2^224, so the row's no-carry-out assumption holds), then add the HIGH half:
+// (T_lo + M p) / R <= p and T_hi < p, so one conditional subtraction finishes.
+template <class P>
+__device__ __forceinline__ void fp_redc_wide(uint32_t* r, const uint32_t* T) {
+  uint32_t ev[8], od[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    ev[i] = T[i];
+    od[i] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    fp_redc_row<P>(ev, od);
+    fp_shift_row(od, ev);   // even = od, odd = ev
+    fp_redc_row<P>(od, ev);
+    fp_shift_row(ev, od);   // even = ev, odd = od
+  }
+  // value = ev (positions 0..7) + od (positions 1..8; od[7] is zero), plus the high half of T
+  uint32_t u[8], o[8];
+  o[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 8; i++) o[i] = od[i - 1];
+  fp_add8c(u, ev, o, 0u);
+  fp_add8c(u, u, T + 8, 0u);
+  fp_final_sub<P>(u);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = u[i];
+}
 #endif  // __CUDA_ARCH__
 
 // ------------------------------------------------------------------------------------------ host 64-bit core
