@@ -144,6 +144,9 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
 int nzcp_intpipe_bench(int device, int iters, double out[4]);
 /* Diagnostic: rates of the carry-chain variants (modes 0..8 of csrc/standalone.cu intpipe_kernel), out[9] = SM count. */
 int nzcp_intpipe_modes(int device, int iters, double out[10]);
+/* Diagnostic: which instructions issue beside IMAD.WIDE (csrc/standalone.cu pipeprobe_kernel).  out[0] = DFMA/s alone;
+ * out[1..3] = IMAD.WIDE/s with DFMA (1:1), xor (1:2), carry-free add (1:2) issued beside it; out[4] = DFMA/s in probe 1. */
+int nzcp_pipe_probe(int device, int iters, double out[5]);
 
 /* ---- host hooks: the library's __host__ __device__ arithmetic compiled for the CPU (what the O(1) host glue runs).
  * Test-only; they let the no-GPU suite pin that code against the oracle.  op: 0 mul, 1 add, 2 sub. */

@@ -66,6 +66,7 @@ SIGNATURES = {
     "nzcp_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t, C.c_int]),
     "nzcp_intpipe_modes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "nzcp_intpipe_bench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "nzcp_pipe_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "nzcp_host_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t]),
     "nzcp_host_scalar_mul": (C.c_int, [C.c_int, _U8P, _U8P, _U8P]),
     "nzcp_host_root_of_unity": (C.c_int, [C.c_int, _U8P]),

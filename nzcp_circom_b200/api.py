@@ -275,6 +275,14 @@ def intpipe_modes(device=0, iters=4096):
     return dict(zip(names, list(out)[:9]))
 
 
+def pipe_probe(device=0, iters=4096):
+    """Which instructions issue beside IMAD.WIDE: -> dict of per-second rates (csrc/standalone.cu pipeprobe_kernel)."""
+    out = (C.c_double * 5)()
+    check(_lib.load().nzcp_pipe_probe(int(device), int(iters), out))
+    names = ("dfma_alone", "wide_with_dfma_1to1", "wide_with_2xor", "wide_with_2add", "dfma_with_wide_1to1")
+    return dict(zip(names, list(out)))
+
+
 def host_field_op(field, op, a, b, n):
     out = bytearray(32 * n)
     check(_lib.load().nzcp_host_field_op(int(field), int(op), addr(a), addr(b), addr(out), int(n)))

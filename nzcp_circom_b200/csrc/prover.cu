@@ -326,22 +326,43 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
   const G1XYZZ d1 = G1XYZZ::from_affine(zk->delta1);
   const G1XYZZ r_d1 = xyzz_mul(d1, r.v), s_d1 = xyzz_mul(d1, s.v), nrs_d1 = xyzz_mul(d1, neg_rs.v);
   const G2XYZZ s_d2 = xyzz_mul(G2XYZZ::from_affine(zk->delta2), s.v);
-  for (int k = 0; k < 4; k++) NZCP_CUDA(cudaStreamSynchronize(p->st_msm[k]));
-  NZCP_CUDA(cudaStreamSynchronize(sm));
-
-  G1XYZZ A, B1, C, H;
+  // The witness MSMs finish well before the H chain (r1cs -> NTT -> sort -> MSM): drain their streams one by one and do
+  // the two result-dependent scalar multiplications (s * pi_A, r * B1') on the host while the GPU is still busy with H.
+  G1XYZZ A, B1, C, H, pi_a, pib1, s_pi_a, r_pib1;
   G2XYZZ B2;
   uint32_t ent_w = 0, ent_h = 0;
   try {
+    NZCP_CUDA(cudaStreamSynchronize(p->st_msm[0]));   // A (its stream waited for the witness sort and its flags)
     ent_w = msm_sort_check(&p->sort_w);
+    A = msm_run_finish_g1(&p->run_a);
+    pi_a = A;
+    xyzz_add(pi_a, G1XYZZ::from_affine(zk->alpha1));
+    xyzz_add(pi_a, r_d1);
+    s_pi_a = xyzz_mul(pi_a, s.v);
+    g1_to_plain_bytes(pi_a, proof->pi_a);
+    NZCP_CUDA(cudaStreamSynchronize(p->st_msm[1]));   // B1
+    B1 = msm_run_finish_g1(&p->run_b1);
+    pib1 = B1;
+    xyzz_add(pib1, G1XYZZ::from_affine(zk->beta1));
+    xyzz_add(pib1, s_d1);
+    r_pib1 = xyzz_mul(pib1, r.v);
+    NZCP_CUDA(cudaStreamSynchronize(p->st_msm[2]));   // B2: pi_B needs nothing else
+    B2 = msm_run_finish_g2(&p->run_b2);
+    G2XYZZ pi_b = B2;
+    xyzz_add(pi_b, G2XYZZ::from_affine(zk->beta2));
+    xyzz_add(pi_b, s_d2);
+    g2_to_plain_bytes(pi_b, proof->pi_b);
+    NZCP_CUDA(cudaStreamSynchronize(p->st_msm[3]));   // C
+    C = msm_run_finish_g1(&p->run_c);
+    NZCP_CUDA(cudaStreamSynchronize(sm));             // H: only its Horner tail, four additions and one inversion remain
     ent_h = msm_sort_check(&p->sort_h);
   } catch (const std::runtime_error& e) {
+    // leave no work in flight behind an error: the prover (and its buffers) may be reused or freed right away
+    for (int k = 0; k < 4; k++) cudaStreamSynchronize(p->st_msm[k]);
+    cudaStreamSynchronize(sm);
+    if (dynamic_cast<const CudaError*>(&e) || dynamic_cast<const ApiError*>(&e)) throw;
     throw ApiError(NZCP_E_RANGE, e.what());
   }
-  A = msm_run_finish_g1(&p->run_a);
-  B1 = msm_run_finish_g1(&p->run_b1);
-  B2 = msm_run_finish_g2(&p->run_b2);
-  C = msm_run_finish_g1(&p->run_c);
   H = msm_run_finish_g1(&p->run_h);
   if (dbg) {
     g1_to_plain_bytes(A, dbg->msm_a);
@@ -371,22 +392,11 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
     dbg->total_ms = el(0, 4);
   }
   // finalisation (tail of groth16Prove): O(1) group operations on the host, as snarkjs does on its main thread
-  G1XYZZ pi_a = A;
-  xyzz_add(pi_a, G1XYZZ::from_affine(zk->alpha1));
-  xyzz_add(pi_a, r_d1);
-  G2XYZZ pi_b = B2;
-  xyzz_add(pi_b, G2XYZZ::from_affine(zk->beta2));
-  xyzz_add(pi_b, s_d2);
-  G1XYZZ pib1 = B1;
-  xyzz_add(pib1, G1XYZZ::from_affine(zk->beta1));
-  xyzz_add(pib1, s_d1);
   G1XYZZ pi_c = C;
   xyzz_add(pi_c, H);
-  xyzz_add(pi_c, xyzz_mul(pi_a, s.v));
-  xyzz_add(pi_c, xyzz_mul(pib1, r.v));
+  xyzz_add(pi_c, s_pi_a);
+  xyzz_add(pi_c, r_pib1);
   xyzz_add(pi_c, nrs_d1);
-  g1_to_plain_bytes(pi_a, proof->pi_a);
-  g2_to_plain_bytes(pi_b, proof->pi_b);
   g1_to_plain_bytes(pi_c, proof->pi_c);
 }
 

@@ -269,6 +269,60 @@ __global__ void __launch_bounds__(256) intpipe_kernel(int iters, uint32_t seed, 
   }
 }
 
+// Pipe-overlap probes behind DESIGN.md's cost model of the multiplier (which instructions issue "for free" next to
+// IMAD.WIDE, and whether the FP64 pipe is a second multiplier worth building a 52-bit-limb product on):
+//   0: fma.rn.f64, 8 independent chains                 -> DFMA/s
+//   1: 4 IMAD.WIDE (2-long carry chains) + 4 DFMA        -> IMAD.WIDE/s with the FP64 pipe busy beside it
+//   2: 4 IMAD.WIDE + 8 lop3 (majority)                      -> IMAD.WIDE/s next to plain ALU work
+//   3: 4 IMAD.WIDE + 8 add.u32 (no carry)                -> IMAD.WIDE/s next to carry-free adds
+template <int mode>
+__global__ void __launch_bounds__(256) pipeprobe_kernel(int iters, uint32_t seed, uint32_t* sink) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+  uint32_t c0 = t, c1 = t ^ 1, c2 = t ^ 2, c3 = t ^ 3, c4 = t ^ 4, c5 = t ^ 5, c6 = t ^ 6, c7 = t ^ 7;
+  double d0 = t, d1 = t + 0.5, d2 = t + 1.5, d3 = t + 2.5, d4 = t + 3.5, d5 = t + 4.5, d6 = t + 5.5, d7 = t + 6.5;
+  const double fx = 1.0 + 1e-9 * (seed & 3), fy = 1e-3 * (1 + (t & 1));
+  uint32_t x = seed | 1, y = seed + t;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (mode == 0) {
+        asm volatile("fma.rn.f64 %0, %0, %8, %9;\n\tfma.rn.f64 %1, %1, %8, %9;\n\tfma.rn.f64 %2, %2, %8, %9;\n\t"
+                     "fma.rn.f64 %3, %3, %8, %9;\n\tfma.rn.f64 %4, %4, %8, %9;\n\tfma.rn.f64 %5, %5, %8, %9;\n\t"
+                     "fma.rn.f64 %6, %6, %8, %9;\n\tfma.rn.f64 %7, %7, %8, %9;"
+                     : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+d"(d6), "+d"(d7)
+                     : "d"(fx), "d"(fy));
+      } else {
+        asm volatile("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.u32 %1, %8, %9, %1;\n\t"
+                     "mad.lo.cc.u32 %2, %8, %9, %2;\n\tmadc.hi.u32 %3, %8, %9, %3;\n\t"
+                     "mad.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.u32 %5, %8, %9, %5;\n\t"
+                     "mad.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
+                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                     : "r"(x), "r"(y));
+        if (mode == 1) {
+          asm volatile("fma.rn.f64 %0, %0, %4, %5;\n\tfma.rn.f64 %1, %1, %4, %5;\n\tfma.rn.f64 %2, %2, %4, %5;\n\t"
+                       "fma.rn.f64 %3, %3, %4, %5;"
+                       : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3) : "d"(fx), "d"(fy));
+        } else if (mode == 2) {
+          // majority(c_k, c_k+1, y): a non-linear 3-input LUT ptxas cannot fold across the ring
+          asm volatile("lop3.b32 %0, %0, %1, %8, 0xE8;\n\tlop3.b32 %1, %1, %2, %8, 0xE8;\n\t"
+                       "lop3.b32 %2, %2, %3, %8, 0xE8;\n\tlop3.b32 %3, %3, %4, %8, 0xE8;\n\t"
+                       "lop3.b32 %4, %4, %5, %8, 0xE8;\n\tlop3.b32 %5, %5, %6, %8, 0xE8;\n\t"
+                       "lop3.b32 %6, %6, %7, %8, 0xE8;\n\tlop3.b32 %7, %7, %0, %8, 0xE8;"
+                       : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7) : "r"(y));
+        } else {
+          asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %1, %1, %2;\n\tadd.u32 %2, %2, %3;\n\tadd.u32 %3, %3, %4;\n\t"
+                       "add.u32 %4, %4, %5;\n\tadd.u32 %5, %5, %6;\n\tadd.u32 %6, %6, %7;\n\tadd.u32 %7, %7, %0;"
+                       : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7));
+        }
+      }
+    }
+  }
+  uint32_t sx = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  double sd = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
+  if (sx == 0x12345678u || sd == 0.123456) sink[0] = sx;
+}
+
 }  // namespace nzcp
 
 using namespace nzcp;
@@ -318,6 +372,38 @@ int nzcp_intpipe_modes(int device, int iters, double out[10]) {
       out[mode] = per_thread * (double)blocks * threads / (best * 1e-3);
     }
     out[9] = (double)prop.multiProcessorCount;
+  });
+}
+
+/* Diagnostic: pipe-overlap probes (csrc/standalone.cu pipeprobe_kernel).  out[0] = DFMA/s alone; out[1..3] =
+ * IMAD.WIDE/s with DFMA (1:1), xor (1:2), carry-free add (1:2) beside it; out[4] = DFMA/s inside probe 1. */
+int nzcp_pipe_probe(int device, int iters, double out[5]) {
+  return api_guard([&] {
+    if (!out || iters < 1) throw ApiError(NZCP_E_ARG, "bad argument");
+    use_device(device);
+    cudaDeviceProp prop;
+    NZCP_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevBuf sink(64);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    for (int mode = 0; mode < 4; mode++) {
+      float best = 1e30f;
+      for (int rep = 0; rep < 4; rep++) {
+        Timer t(0);
+        switch (mode) {
+          case 0: pipeprobe_kernel<0><<<blocks, threads>>>(iters, 777u + rep, sink.as<uint32_t>()); break;
+          case 1: pipeprobe_kernel<1><<<blocks, threads>>>(iters, 777u + rep, sink.as<uint32_t>()); break;
+          case 2: pipeprobe_kernel<2><<<blocks, threads>>>(iters, 777u + rep, sink.as<uint32_t>()); break;
+          default: pipeprobe_kernel<3><<<blocks, threads>>>(iters, 777u + rep, sink.as<uint32_t>()); break;
+        }
+        NZCP_LAUNCH_CHECK();
+        float ms = t.stop();
+        if (rep && ms < best) best = ms;
+      }
+      // per iteration and thread: mode 0 = 64 DFMA; modes 1..3 = 32 IMAD.WIDE (+ 32 DFMA in mode 1)
+      double per_thread = (mode == 0 ? 64.0 : 32.0) * iters;
+      out[mode] = per_thread * (double)blocks * threads / (best * 1e-3);
+    }
+    out[4] = out[1];
   });
 }
 
