@@ -63,6 +63,7 @@ struct R1csDevice {
   uint32_t* row_ptr = nullptr;  // 2n+1 entries: rows 0..n-1 = A, n..2n-1 = B
   uint32_t* col = nullptr;      // signal index per coefficient
   Fr* val = nullptr;            // coef * R^2 mod r exactly as stored in zkey section 4
+  uint32_t* order = nullptr;    // thread t evaluates constraint order[t]: each 128-row block sorted by row length
 };
 // abc = [A_T | B_T | C_T], each n Montgomery-form Fr.  witness: plain Fr, n_vars entries.
 void r1cs_eval(const R1csDevice& m, const Fr* witness, Fr* abc, cudaStream_t st);

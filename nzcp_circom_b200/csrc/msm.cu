@@ -37,6 +37,7 @@ namespace nzcp {
 #define NZCP_TASK_LEN_MAX 64
 #endif
 static constexpr int kTaskLenMax = NZCP_TASK_LEN_MAX;  // entries per accumulate task: 8..64, picked on the device from the entry
+static_assert((NZCP_TASK_LEN_MAX & (NZCP_TASK_LEN_MAX - 1)) == 0 && NZCP_TASK_LEN_MAX >= 8, "task length must be a power of two");
 static constexpr int kTaskLenMin = 8;      //   count so that the tasks about fill the GPU once (flags[4])
 #ifndef NZCP_TARGET_TASKS
 #define NZCP_TARGET_TASKS (148 * 640)
@@ -264,42 +265,64 @@ msm_scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restric
 
 // Single-block exclusive scan: out[i] = sum_{j<i} f(in[j]), out[n] = total.  f = identity or ceil(x / task_len).
 // TASKS mode first picks the task length from the entry total in flags[3] and publishes it in flags[4].
+// Chunks of 4096 values: coalesced loads (four consecutive values per thread), warp-shuffle scans, one carry between
+// chunks -- this kernel sits alone on the latency path of every sort (2^15 buckets = 8 chunks).
 template <bool TASKS>
 __global__ void __launch_bounds__(1024)
 msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ total,
                 uint32_t* __restrict__ flags) {
-  __shared__ uint32_t sums[1024];
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t chunk_total;
   uint32_t tl = kTaskLenMax;
   if (TASKS) {
     uint32_t per_thread = flags[3] / kTargetTasks;
     while (tl > (uint32_t)kTaskLenMin && tl > per_thread) tl >>= 1;
     if (threadIdx.x == 0) flags[4] = tl;
   }
-  uint32_t per = (n + 1023) / 1024;
-  uint32_t b = threadIdx.x * per;
-  uint32_t e = b + per < n ? b + per : n;
-  uint32_t acc = 0;
-  for (uint32_t i = b; i < e; i++) {
-    uint32_t v = in[i];
-    acc += TASKS ? (v + tl - 1) / tl : v;
-  }
-  sums[threadIdx.x] = acc;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    uint32_t v = threadIdx.x >= (uint32_t)off ? sums[threadIdx.x - off] : 0;
+  const uint32_t tsh = 31 - __clz(tl);   // task lengths are powers of two: ceil(v / tl) without the integer division
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n; base += 4096) {
+    const uint32_t i0 = base + threadIdx.x * 4;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t x = i0 + k < n ? in[i0 + k] : 0u;
+      v[k] = TASKS ? (x + tl - 1) >> tsh : x;
+      s += v[k];
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    sums[threadIdx.x] += v;
+    if (warp == 0) {
+      const uint32_t w = wsum[lane];
+      uint32_t z = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, z, d);
+        if (lane >= (uint32_t)d) z += y;
+      }
+      wsum[lane] = z - w;
+      if (lane == 31) chunk_total = z;
+    }
+    __syncthreads();
+    uint32_t run = carry + wsum[warp] + (incl - s);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < n) out[i0 + k] = run;
+      run += v[k];
+    }
+    carry += chunk_total;
     __syncthreads();
   }
-  uint32_t run = threadIdx.x ? sums[threadIdx.x - 1] : 0;
-  for (uint32_t i = b; i < e; i++) {
-    out[i] = run;
-    uint32_t v = in[i];
-    run += TASKS ? (v + tl - 1) / tl : v;
-  }
-  if (threadIdx.x == 1023) {
-    out[n] = sums[1023];
-    if (total) *total = sums[1023];
+  if (threadIdx.x == 0) {
+    out[n] = carry;
+    if (total) *total = carry;
   }
 }
 
@@ -343,6 +366,9 @@ __device__ __forceinline__ void prefetch_l1(const T* p) {
 template <class F> struct AccumOcc { static constexpr int kBlocks = 5; };   // G1: <= 102 registers
 template <> struct AccumOcc<Fq2> { static constexpr int kBlocks = NZCP_G2_ACC_BLOCKS; };
 
+// DRAM traffic (ncu): 128 bytes per 64-byte G1 point, 1.05 x 128 bytes per G2 point -- random reads cost a full 128-byte
+// line on this part.  Tried and measured without effect on bytes or time: staging the point with 16-byte cp.async
+// (LDGSTS.BYPASS) instead of the L1 prefetch, and cudaLimitMaxL2FetchGranularity = 32 / 64.
 template <class F>
 __global__ void __launch_bounds__(128, AccumOcc<F>::kBlocks)
 msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,

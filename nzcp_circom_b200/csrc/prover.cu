@@ -7,6 +7,7 @@
 // Differences that do not change any output bit: sections 4-9 are parsed and uploaded once per zkey instead of
 // re-read per proof; the COO coefficient list is regrouped to CSR; the four witness MSMs run on their own streams
 // concurrently with the H pipeline.
+#include <stdlib.h>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -103,6 +104,7 @@ static void zkey_release(nzcp_zkey* zk) {
   cudaFree(zk->r1cs.row_ptr);
   cudaFree(zk->r1cs.col);
   cudaFree(zk->r1cs.val);
+  cudaFree(zk->r1cs.order);
   msm_table_destroy(&zk->tab_a);
   msm_table_destroy(&zk->tab_b1);
   msm_table_destroy(&zk->tab_b2);
@@ -187,6 +189,27 @@ static nzcp_zkey* zkey_load_impl(const uint8_t* b, size_t len, int device) {
   zk->r1cs.row_ptr = upload<uint32_t>(row_ptr.data(), row_ptr.size() * 4, &tot);
   zk->r1cs.col = upload<uint32_t>(col.data(), nc * 4, &tot);
   zk->r1cs.val = upload<Fr>(val.data(), nc * 32, &tot);
+  // Constraint order for the evaluation kernel (one thread per constraint): inside every block of 128 consecutive
+  // constraints the rows are handed to threads longest first, so the 32 lanes of a warp walk rows of similar length
+  // (NZCP rows have 1..8 terms; unsorted, a warp runs as long as its longest row while the average is under 3).
+  {
+    std::vector<uint32_t> order(n);
+    uint32_t key[128];
+    for (size_t b0 = 0; b0 < n; b0 += 128) {
+      const size_t cnt = n - b0 < 128 ? n - b0 : 128;
+      uint32_t hist[64] = {0};
+      for (size_t j = 0; j < cnt; j++) {
+        const size_t i = b0 + j;
+        uint32_t len = (row_ptr[i + 1] - row_ptr[i]) + (row_ptr[n + i + 1] - row_ptr[n + i]);
+        key[j] = len > 63 ? 63 : len;
+        hist[key[j]]++;
+      }
+      uint32_t start[64], run = 0;
+      for (int l = 63; l >= 0; l--) { start[l] = run; run += hist[l]; }   // counting sort, longest first, stable
+      for (size_t j = 0; j < cnt; j++) order[b0 + start[key[j]]++] = (uint32_t)(b0 + j);
+    }
+    zk->r1cs.order = upload<uint32_t>(order.data(), (size_t)n * 4, &tot);
+  }
   // sections 5-9 -> window tables (one-time expansion; the raw section is only staged)
   zk->c_w = msm_pick_window(m);
   zk->c_h = msm_pick_window(n);
@@ -292,6 +315,18 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
     d_w = p->d_wtns;
   }
   NZCP_CUDA(cudaEventRecord(p->ev[1], sm));
+  // Launch order = the proof's critical path first: r1cs -> NTT -> join -> H sort go out before the ~40 launches of the
+  // witness sort and MSMs, so the GPU starts on the chain that cannot be shortened while the host is still enqueueing
+  // the filler (the four witness MSMs, 3 ms of full-GPU work).  Measured alternatives (lone proof):
+  // a high-priority stream for this chain and gating the witness accumulations behind the NTT or the H sort all lose --
+  // the sort's whole-SM blocks cannot be placed while accumulate blocks keep refilling the SMs, whatever the priority.
+  r1cs_eval(zk->r1cs, d_w, p->d_abc, sm);
+  NZCP_CUDA(cudaEventRecord(p->ev[2], sm));
+  ntt_coset_pipeline(zk->dom, p->d_abc, 3, sm);
+  ntt_join_abc(p->d_abc, p->d_abc + n, p->d_abc + 2 * n, p->d_h, n, sm);
+  NZCP_CUDA(cudaEventRecord(p->ev[3], sm));
+  msm_sort_launch(&p->sort_h, p->d_h, n, sm);
+  NZCP_CUDA(cudaEventRecord(p->ev[14], sm));
   // The four witness MSMs (snarkjs order: A, B1, B2, C) share ONE bucket sort of the witness; the C table is
   // front-padded with nPublic+1 infinity points so it is indexed by wire number like the others.
   // B2 (G2, the longest) is sorted for on its own stream and launched first.
@@ -308,14 +343,6 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
     msm_run_launch(jobs[k].run, &p->sort_w, jobs[k].tab, st);
     NZCP_CUDA(cudaEventRecord(p->ev[7 + 2 * jobs[k].stream], st));
   }
-  // H pipeline on the main stream
-  r1cs_eval(zk->r1cs, d_w, p->d_abc, sm);
-  NZCP_CUDA(cudaEventRecord(p->ev[2], sm));
-  ntt_coset_pipeline(zk->dom, p->d_abc, 3, sm);
-  ntt_join_abc(p->d_abc, p->d_abc + n, p->d_abc + 2 * n, p->d_h, n, sm);
-  NZCP_CUDA(cudaEventRecord(p->ev[3], sm));
-  msm_sort_launch(&p->sort_h, p->d_h, n, sm);
-  NZCP_CUDA(cudaEventRecord(p->ev[14], sm));
   msm_run_launch(&p->run_h, &p->sort_h, &zk->tab_h, sm);
   NZCP_CUDA(cudaEventRecord(p->ev[4], sm));
   if (dbg && dbg->h_scalars) NZCP_CUDA(cudaMemcpyAsync(dbg->h_scalars, p->d_h, n * sizeof(Fr), cudaMemcpyDeviceToHost, sm));

@@ -9,6 +9,8 @@
 // B200 design.  The COO records are converted once, at zkey load, to CSR (rows 0..n-1 = A, n..2n-1 = B), so a
 // proof needs no atomics and the result does not depend on record order.  One thread owns constraint i: it walks
 // row i of A and row i of B (<= 8 terms each for the NZCP shape), then writes A_T[i], B_T[i] and their product.
+// Threads take the constraints of their 128-row block longest first (order[], built at zkey load), so a warp's lanes
+// walk rows of similar length instead of idling behind the longest one; the stores stay inside the block's 12 KB.
 // HBM-bound: 36 B per coefficient (value + column) + a 32 B gathered witness word, 96 B written per constraint.
 #include "common.cuh"
 
@@ -38,9 +40,10 @@ __device__ __forceinline__ Fr row_dot(const uint32_t* __restrict__ row_ptr, cons
 
 __global__ void __launch_bounds__(128)
 r1cs_eval_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, const Fr* __restrict__ val,
-                 const Fr* __restrict__ w, Fr* __restrict__ abc, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                 const uint32_t* __restrict__ order, const Fr* __restrict__ w, Fr* __restrict__ abc, uint32_t n) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t i = order[t];
   Fr a = row_dot(row_ptr, col, val, w, i);
   Fr b = row_dot(row_ptr, col, val, w, n + i);
   st_fr(abc + i, a);
@@ -49,7 +52,7 @@ r1cs_eval_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restric
 }
 
 void r1cs_eval(const R1csDevice& m, const Fr* witness, Fr* abc, cudaStream_t st) {
-  r1cs_eval_kernel<<<div_up(m.n, 128), 128, 0, st>>>(m.row_ptr, m.col, m.val, witness, abc, m.n);
+  r1cs_eval_kernel<<<div_up(m.n, 128), 128, 0, st>>>(m.row_ptr, m.col, m.val, m.order, witness, abc, m.n);
   NZCP_LAUNCH_CHECK();
 }
 
