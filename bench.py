@@ -322,11 +322,11 @@ def roofline_block(dbg, zk, hbm, peak_src):
         out["roofline"] = {
             "kernel": "msm_accumulate_kernel<Fq> (H MSM bucket accumulation)", "bound": "int32-mul-pipe",
             "achieved": ach / 1e9, "peak": peak_mul / 1e9, "unit": "GFqmul/s", "frac": ach / peak_mul,
-            "traffic": 2.31e9 * ent / 16776933.0,
+            "traffic": 2.29e9 * ent / 16776933.0,
             "launch_ms": acc_ms, "algorithmic_fq_mul": ent * 10,
-            "traffic_note": "ncu --set full (profiles/r01_ncu_accumulate_ntt_full.md): dram read+write 2.31 GB per launch vs "
+            "traffic_note": "ncu --set full (profiles/r01_ncu_accumulate_ntt_full.md): dram read+write 2.29 GB per launch vs "
                             "1.14 GB algorithmic (68 B/entry): 64-B points fetched as 128-B lines; DRAM at 10 % of peak, "
-                            "fmaheavy (IMAD.WIDE) pipe 88 % active -- the kernel sits on the multiplier, not on memory",
+                            "fmaheavy (IMAD.WIDE) pipe 85 % active -- the kernel sits on the multiplier, not on memory",
             "peak_source": "measured here: %.2f T IMAD.WIDE.U32/s (32 per SM per clock, half the 32-bit IMAD rate) / 128 "
                            "32x32 products per 254-bit Montgomery mul; a register-only Fq mul microbenchmark reaches "
                            "%.1f GFqmul/s" % (ip["imad_wide_per_s"] / 1e12, ip["fq_mul_per_s"] / 1e9),
