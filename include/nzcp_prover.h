@@ -135,9 +135,15 @@ int nzcp_msm(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int 
 /* Device self-test of the field / curve arithmetic against the host build of the same code; returns the number of
  * mismatches in *n_bad (0 = pass). */
 int nzcp_selftest(int device, uint64_t seed, uint32_t n_cases, uint32_t* n_bad);
-/* Element-wise Fr/Fq ops on the device, for limb-exact parity tests: op 0 mul, 1 add, 2 sub (Montgomery-form in/out),
+/* Element-wise Fr/Fq ops on the device, for limb-exact parity tests: op 0 mul, 1 add, 2 sub (3..5: the portable code paths), 6 inverse by division steps, 7 Fermat inverse (Montgomery-form in/out),
  * field 0 = Fr, 1 = Fq. */
 int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int device);
+
+/* Tuning knobs for experiments and tests (process-wide, read when a plan is created / a run is launched):
+ *   "msm_rounds"  batched-affine pair rounds per MSM: -1 = automatic (by size), 0..3 forced
+ *   "prover_rounds_w" / "prover_rounds_h"  the same for a prover's witness MSMs / H MSM (read by nzcp_prover_create)
+ *   "pair_k1" / "pair_k2" / "pair_k3"  additions sharing one inversion per thread in round 1 / 2 / 3: 16, 32 or 64 */
+int nzcp_tuning_set(const char* name, int value);
 
 /* Integer-pipe microbenchmark (the MSM / NTT roofline denominator): out[0] = IMAD.WIDE.U32 (32x32->64 multiply-add) per
  * second, out[1] = 32-bit IMAD per second, out[2] = dependent-chain Fq Montgomery products per second, out[3] = SM count. */
@@ -149,10 +155,16 @@ int nzcp_intpipe_modes(int device, int iters, double out[10]);
 int nzcp_pipe_probe(int device, int iters, double out[5]);
 
 /* ---- host hooks: the library's __host__ __device__ arithmetic compiled for the CPU (what the O(1) host glue runs).
- * Test-only; they let the no-GPU suite pin that code against the oracle.  op: 0 mul, 1 add, 2 sub. */
+ * Test-only; they let the no-GPU suite pin that code against the oracle.  op: 0 mul, 1 add, 2 sub, 3 inverse by
+ * division steps (fp_inv_fast; b ignored), 4 inverse by the Fermat ladder. */
 int nzcp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* k * base (Montgomery affine base as in the zkey, NULL = the group generator); out = plain affine. */
 int nzcp_host_scalar_mul(int g2, const uint8_t* base_mont, const uint8_t* scalar, uint8_t* out_plain);
+/* The MSM data path INCLUDING the batched-affine pair rounds of csrc/msm_pair.cuh, executed on the CPU with the same
+ * __host__ __device__ code the kernels run (rounds = 0..3 pair rounds, adds_per_thread = 4, 16, 32 or 64).  Lets the
+ * no-GPU suite check the rounds' index arithmetic and special-pair handling against the oracle.  out = plain affine. */
+int nzcp_host_msm_sim(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int g2, int window_bits, int rounds,
+                      int adds_per_thread, uint8_t* out);
 /* Fr.w[k] of ffjavascript (plain form). */
 int nzcp_host_root_of_unity(int k, uint8_t* out_plain);
 

@@ -70,6 +70,8 @@ SIGNATURES = {
     "nzcp_host_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t]),
     "nzcp_host_scalar_mul": (C.c_int, [C.c_int, _U8P, _U8P, _U8P]),
     "nzcp_host_root_of_unity": (C.c_int, [C.c_int, _U8P]),
+    "nzcp_host_msm_sim": (C.c_int, [_U8P, _U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _U8P]),
+    "nzcp_tuning_set": (C.c_int, [C.c_char_p, C.c_int]),
     "nzcp_synth_points": (C.c_int, [C.c_uint64, C.c_size_t, C.c_int, C.c_int, _U8P]),
     "nzcp_synth_create": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "nzcp_synth_free": (None, [_P]),

@@ -296,6 +296,19 @@ def host_scalar_mul(g2, base_mont, scalar):
     return bytes(out)
 
 
+def host_msm_sim(bases, scalars, n_points, g2=False, window_bits=8, rounds=1, adds_per_thread=4):
+    """CPU run of the MSM data path incl. the batched-affine pair rounds (same code as the kernels) -> plain affine."""
+    out = bytearray(128 if g2 else 64)
+    check(_lib.load().nzcp_host_msm_sim(addr(bases), addr(scalars), int(n_points), int(bool(g2)), int(window_bits),
+                                        int(rounds), int(adds_per_thread), addr(out)))
+    return bytes(out)
+
+
+def tuning_set(name, value):
+    """Process-wide tuning knob (see include/nzcp_prover.h nzcp_tuning_set)."""
+    check(_lib.load().nzcp_tuning_set(name.encode(), int(value)))
+
+
 def host_root_of_unity(k):
     out = bytearray(32)
     check(_lib.load().nzcp_host_root_of_unity(int(k), addr(out)))

@@ -85,6 +85,8 @@ int msm_num_windows(int c);
 void msm_table_create(MsmTable* t, const void* d_bases, size_t n_src, size_t pad_front, bool g2, int c, cudaStream_t st);
 void msm_table_destroy(MsmTable* t);
 
+static constexpr int kMsmMaxRounds = 3;
+
 // Bucket sort of one scalar vector: signed c-bit digits -> (table index | sign) entries grouped by bucket, cut into
 // tasks of <= kTaskLen entries.  Shared by every MSM that uses the same scalars (A, B1, B2, C all use the witness).
 struct MsmSort {
@@ -96,17 +98,26 @@ struct MsmSort {
   uint32_t* counts = nullptr;
   uint32_t* offsets = nullptr;
   uint32_t* cursors = nullptr;
-  uint32_t* bcount = nullptr;      // entries per bucket
   uint32_t* block_sums = nullptr;  // scratch of the multi-block scan
   uint32_t* entries = nullptr;
   uint32_t* task_off = nullptr;
   uint2* tasks = nullptr;
-  uint32_t* flags = nullptr;      // [1] error flags, [2] total tasks, [3] total entries
+  uint32_t* flags = nullptr;      // [1] error flags, [2] total tasks, [3] total entries, [4] task length,
+                                  // [5] points left after the affine pair rounds (= [3] when rounds == 0)
   uint32_t* flags_host = nullptr; // pinned mirror
   size_t max_tasks = 0;
   size_t scratch_bytes = 0;
+  // Batched-affine pair rounds (msm.cu "pair rounds"): round r halves every bucket's point list (ceil(len / 2)) with
+  // affine additions that share one field inversion per thread.  round_off[r * (n_buckets + 1) + b] = first slot of
+  // bucket b in the round-r point array (r = 0: the entry list itself, compact copy of `offsets`); red_count[b] =
+  // points of bucket b after the last round -- what the task list and the XYZZ accumulation then work on.
+  int rounds = 0;
+  uint32_t* round_off = nullptr;
+  uint32_t* red_count = nullptr;
+  size_t round_max[kMsmMaxRounds + 1] = {0, 0, 0, 0};   // upper bound of the point count after round r
 };
-void msm_sort_create(MsmSort* s, size_t n_points, int c);
+int msm_pick_rounds(size_t n_points, int c);
+void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds = -1);   // rounds < 0: msm_pick_rounds
 void msm_sort_destroy(MsmSort* s);
 void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_t st);
 // After the stream drained: throws if the device flagged a scalar >= r.  Returns the number of non-zero digits.
@@ -125,7 +136,9 @@ struct MsmRun {
   void* chunk_partial = nullptr;
   void* out = nullptr;        // device: S_0 .. S_{n_digits-1}, T
   void* out_host = nullptr;   // pinned
-  cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;  // around the accumulate kernel (roofline timing)
+  cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;  // around the bucket accumulation (pair rounds + XYZZ kernel)
+  void* round_pts[2] = {nullptr, nullptr};   // affine point arrays of the pair rounds (ping-pong)
+  void* round_prefix = nullptr;              // prefix products of the shared inversion, [step][thread]
   size_t scratch_bytes = 0;
 };
 void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2);

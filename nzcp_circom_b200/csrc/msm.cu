@@ -16,16 +16,23 @@
 //     1 digits/count   signed c-bit digits (c = 16 at 2^20), histogram over 2^15 buckets in per-SM shared memory
 //     2 scan           exclusive prefix sum of the bucket counts
 //     3 scatter        (w * n + i) | sign << 31 written into the bucket's slot range
-//     4 tasks          every bucket is cut into tasks of <= 64 entries, so the 0/1-heavy witness distribution
-//                      (a quarter of all wires land in bucket "1") still load-balances
+//     4 plan + tasks   bucket offsets of the pair rounds (below); every bucket's remaining list is cut into tasks of <= 64
+//                      points, so the 0/1-heavy witness distribution (a quarter of all wires land in bucket "1") still
+//                      load-balances
 //   run (per base section):
-//     5 accumulate     one thread per task: XYZZ accumulator in registers, 8M+2S mixed adds, table entries gathered
-//                      by index with the next one prefetched into L1 during the current add
+//     5a pair rounds   (large MSMs) up to three batched-affine rounds: each halves every bucket's list with affine
+//                      additions that share one inversion per thread (msm_pair.cuh): 6 + 50/K products per addition
+//                      instead of 10, for 7/8 of all additions
+//     5b accumulate    one thread per task: XYZZ accumulator in registers, 8M+2S mixed adds over what the rounds left
+//                      (or, without rounds, over table entries gathered by index, next one prefetched into L1)
 //     6 combine        one thread per bucket sums its (<= 16) task partials; buckets with more go through a two-stage
 //                      block-wide sum (chunks of 512 partials, then the chunk results)
 //     7 reduce         sum_v v * B_v through marginal sums per base-32 digit of the bucket id (two launches, no level tree)
 //     8 host           T + sum_k 32^k S_k: ten doublings and four additions
+#include <atomic>
+
 #include "common.cuh"
+#include "msm_pair.cuh"
 
 #ifndef NZCP_G2_ACC_BLOCKS
 #define NZCP_G2_ACC_BLOCKS 3
@@ -275,7 +282,7 @@ msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uin
   __shared__ uint32_t chunk_total;
   uint32_t tl = kTaskLenMax;
   if (TASKS) {
-    uint32_t per_thread = flags[3] / kTargetTasks;
+    uint32_t per_thread = flags[5] / kTargetTasks;   // points left after the pair rounds
     while (tl > (uint32_t)kTaskLenMin && tl > per_thread) tl >>= 1;
     if (threadIdx.x == 0) flags[4] = tl;
   }
@@ -326,20 +333,86 @@ msm_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uin
   }
 }
 
-// Bucket totals from the scanned sub-counters: bcount[b] = offsets[(b+1)*n_copies] - offsets[b*n_copies].
-__global__ void __launch_bounds__(256)
-msm_bucket_count_kernel(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ bcount, uint32_t n_buckets,
-                        uint32_t n_copies) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_buckets) return;
-  bcount[b] = offsets[(b + 1) * n_copies] - offsets[b * n_copies];
+// Round plan (one block; it sits where the per-bucket count kernel used to): from the scanned sub-counters take every
+// bucket's entry count len_0, derive len_r = ceil(len_{r-1} / 2) for the R pair rounds, and write the R + 1 exclusive
+// prefix sums round_off[r][b] (round_off[r][n_buckets] = points in round r) plus red_count[b] = len_R.
+// Chunks of 4096 buckets, four per thread, warp-shuffle scans of all R + 1 channels at once.
+template <int R>
+__global__ void __launch_bounds__(1024)
+msm_round_plan_kernel(const uint32_t* __restrict__ offsets, uint32_t n_copies, uint32_t n_buckets,
+                      uint32_t* __restrict__ round_off, uint32_t* __restrict__ red_count, uint32_t* __restrict__ flags) {
+  constexpr int C = R + 1;
+  __shared__ uint32_t wsum[C][32];
+  __shared__ uint32_t chunk_total[C];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t pitch = n_buckets + 1;
+  uint32_t carry[C];
+#pragma unroll
+  for (int r = 0; r < C; r++) carry[r] = 0;
+  for (uint32_t base = 0; base < n_buckets; base += 4096) {
+    const uint32_t b0 = base + threadIdx.x * 4;
+    uint32_t v[C][4], sum[C], incl[C];
+#pragma unroll
+    for (int r = 0; r < C; r++) sum[r] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t b = b0 + k;
+      uint32_t len = b < n_buckets ? offsets[(size_t)(b + 1) * n_copies] - offsets[(size_t)b * n_copies] : 0u;
+#pragma unroll
+      for (int r = 0; r < C; r++) {
+        v[r][k] = len;
+        sum[r] += len;
+        len = (len + 1) >> 1;
+      }
+      if (b < n_buckets) red_count[b] = v[R][k];
+    }
+#pragma unroll
+    for (int r = 0; r < C; r++) {
+      incl[r] = sum[r];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl[r], d);
+        if (lane >= (uint32_t)d) incl[r] += y;
+      }
+      if (lane == 31) wsum[r][warp] = incl[r];
+    }
+    __syncthreads();
+    if (warp < (uint32_t)C) {
+      const uint32_t w = wsum[warp][lane];
+      uint32_t z = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, z, d);
+        if (lane >= (uint32_t)d) z += y;
+      }
+      wsum[warp][lane] = z - w;
+      if (lane == 31) chunk_total[warp] = z;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < C; r++) {
+      uint32_t run = carry[r] + wsum[r][warp] + (incl[r] - sum[r]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (b0 + k < n_buckets) round_off[(size_t)r * pitch + b0 + k] = run;
+        run += v[r][k];
+      }
+      carry[r] += chunk_total[r];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < C; r++) round_off[(size_t)r * pitch + n_buckets] = carry[r];
+    flags[5] = carry[R];
+  }
 }
 
 // One thread per task: find its bucket by binary search in task_off, then (first entry, length).
 __global__ void __launch_bounds__(256)
 msm_task_fill_kernel(const uint32_t* __restrict__ bcount, const uint32_t* __restrict__ offsets,
                      const uint32_t* __restrict__ task_off, uint2* __restrict__ tasks, uint32_t n_buckets,
-                     uint32_t n_copies, const uint32_t* __restrict__ flags) {
+                     const uint32_t* __restrict__ flags) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= flags[2]) return;
   const uint32_t tl = flags[4];
@@ -353,7 +426,7 @@ msm_task_fill_kernel(const uint32_t* __restrict__ bcount, const uint32_t* __rest
   (void)tl;
   const uint32_t k = task_off[lo + 1] - task_off[lo], j = t - task_off[lo];
   const uint32_t cnt = bcount[lo], base = cnt / k, rem = cnt % k;
-  tasks[t] = make_uint2(offsets[lo * n_copies] + j * base + (j < rem ? j : rem), base + (j < rem ? 1u : 0u));
+  tasks[t] = make_uint2(offsets[lo] + j * base + (j < rem ? j : rem), base + (j < rem ? 1u : 0u));
 }
 
 // ------------------------------------------------------------------------------------------------ run
@@ -390,6 +463,33 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
     e = en;
   }
   partial[t] = acc;
+}
+
+// The same accumulation over what the pair rounds left: the task's points are contiguous in the last round's array.
+template <class F>
+__global__ void __launch_bounds__(128, AccumOcc<F>::kBlocks)
+msm_accumulate_pts_kernel(const Affine<F>* __restrict__ pts, const uint2* __restrict__ tasks,
+                          const uint32_t* __restrict__ flags, XYZZ<F>* __restrict__ partial) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= flags[2]) return;
+  uint2 tk = tasks[t];
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t k = 0; k < tk.y; k++) {
+    Affine<F> q = pts[tk.x + k];
+    if (!q.is_inf()) xyzz_madd(acc, q, false);
+  }
+  partial[t] = acc;
+}
+
+// One pair round (msm_pair.cuh): thread t produces K consecutive points of the round.
+template <class F, bool FROM_TABLE, int K>
+__global__ void __launch_bounds__(128)
+msm_pair_round_kernel(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
+                      const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t n_buckets,
+                      Affine<F>* __restrict__ dst, F* __restrict__ scratch) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  PairSource<F, FROM_TABLE> ps{src, entries};
+  msm_pair_round_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, dst, scratch);
 }
 
 template <class T>
@@ -593,6 +693,24 @@ int msm_num_windows(int c) {
   return w;
 }
 
+// Tuning knobs (nzcp_tuning_set): pair rounds per MSM (-1 = msm_pick_rounds) and additions per thread in round 1, 2, 3.
+std::atomic<int> g_tune_rounds{-1};
+std::atomic<int> g_tune_rounds_w{-1}, g_tune_rounds_h{-1};   // prover: witness MSMs / H MSM (-1 = default)
+std::atomic<int> g_tune_pair_k[kMsmMaxRounds] = {{32}, {32}, {32}};
+
+// Pair rounds pay when the buckets are long: every round costs a launch and leaves ceil(len / 2) points per bucket,
+// and the XYZZ tail wants >= ~16 points per bucket to keep its threads busy.
+int msm_pick_rounds(size_t n_points, int c) {
+  const int forced = g_tune_rounds.load();
+  if (forced >= 0) return forced > kMsmMaxRounds ? kMsmMaxRounds : forced;
+  const size_t entries = (size_t)msm_num_windows(c) * n_points;
+  if (entries < ((size_t)1 << 21)) return 0;
+  const size_t per_bucket = entries >> (c - 1);
+  int r = 0;
+  while (r < kMsmMaxRounds && (per_bucket >> (r + 1)) >= 32) r++;
+  return r;
+}
+
 template <class T>
 static T* dev_alloc(size_t count, size_t* total) {
   T* p = nullptr;
@@ -629,11 +747,12 @@ void msm_table_destroy(MsmTable* t) {
   *t = MsmTable();
 }
 
-void msm_sort_create(MsmSort* s, size_t n_points, int c) {
+void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds) {
   *s = MsmSort();
   if (c < 2 || c > 20) throw std::runtime_error("msm: window size out of range");
   s->n_points = n_points;
   s->c = c;
+  s->rounds = rounds < 0 ? msm_pick_rounds(n_points, c) : (rounds > kMsmMaxRounds ? kMsmMaxRounds : rounds);
   s->n_windows = msm_num_windows(c);
   s->n_buckets = (size_t)1 << (c - 1);
   size_t max_entries = (size_t)s->n_windows * n_points;
@@ -649,7 +768,10 @@ void msm_sort_create(MsmSort* s, size_t n_points, int c) {
   s->counts = dev_alloc<uint32_t>(n_ctr + 1, &tot);
   s->offsets = dev_alloc<uint32_t>(n_ctr + 1, &tot);
   s->cursors = dev_alloc<uint32_t>(n_ctr + 1, &tot);
-  s->bcount = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
+  s->red_count = dev_alloc<uint32_t>(s->n_buckets + 1, &tot);
+  s->round_off = dev_alloc<uint32_t>((size_t)(kMsmMaxRounds + 1) * (s->n_buckets + 1), &tot);
+  s->round_max[0] = max_entries;
+  for (int r = 1; r <= kMsmMaxRounds; r++) s->round_max[r] = (s->round_max[r - 1] + s->n_buckets) / 2 + 1;
   s->block_sums = dev_alloc<uint32_t>(2 * (n_ctr / kScanBlock + 2), &tot);
   if (s->smem_hist) {  // function attributes are per device: set them whenever a plan is created on the current one
     NZCP_CUDA(cudaFuncSetAttribute(msm_digits_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHistBuckets * 4));
@@ -668,7 +790,8 @@ void msm_sort_destroy(MsmSort* s) {
   cudaFree(s->counts);
   cudaFree(s->offsets);
   cudaFree(s->cursors);
-  cudaFree(s->bcount);
+  cudaFree(s->red_count);
+  cudaFree(s->round_off);
   cudaFree(s->block_sums);
   cudaFree(s->entries);
   cudaFree(s->task_off);
@@ -718,12 +841,17 @@ void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_
     else
       msm_digits_kernel<true><<<gp, 256, 0, st>>>(scalars, dp, s->cursors, s->entries, s->flags);
     NZCP_LAUNCH_CHECK();
-    msm_bucket_count_kernel<<<div_up(nb, 256), 256, 0, st>>>(s->offsets, s->bcount, nb, n_copies);
+    switch (s->rounds) {
+      case 0: msm_round_plan_kernel<0><<<1, 1024, 0, st>>>(s->offsets, n_copies, nb, s->round_off, s->red_count, s->flags); break;
+      case 1: msm_round_plan_kernel<1><<<1, 1024, 0, st>>>(s->offsets, n_copies, nb, s->round_off, s->red_count, s->flags); break;
+      case 2: msm_round_plan_kernel<2><<<1, 1024, 0, st>>>(s->offsets, n_copies, nb, s->round_off, s->red_count, s->flags); break;
+      default: msm_round_plan_kernel<3><<<1, 1024, 0, st>>>(s->offsets, n_copies, nb, s->round_off, s->red_count, s->flags); break;
+    }
     NZCP_LAUNCH_CHECK();
-    msm_scan_kernel<true><<<1, 1024, 0, st>>>(s->bcount, s->task_off, nb, s->flags + 2, s->flags);
+    msm_scan_kernel<true><<<1, 1024, 0, st>>>(s->red_count, s->task_off, nb, s->flags + 2, s->flags);
     NZCP_LAUNCH_CHECK();
-    msm_task_fill_kernel<<<div_up(s->max_tasks, 256), 256, 0, st>>>(s->bcount, s->offsets, s->task_off, s->tasks, nb, n_copies,
-                                                                     s->flags);
+    msm_task_fill_kernel<<<div_up(s->max_tasks, 256), 256, 0, st>>>(s->red_count, s->round_off + (size_t)s->rounds * (nb + 1),
+                                                                     s->task_off, s->tasks, nb, s->flags);
     NZCP_LAUNCH_CHECK();
   } else {
     NZCP_CUDA(cudaMemsetAsync(s->task_off, 0, (nb + 1) * sizeof(uint32_t), st));
@@ -760,6 +888,12 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
   NZCP_CUDA(cudaMallocHost(&r->out_host, (kMaxDigits + 1) * psz));
   memset(r->out_host, 0, (kMaxDigits + 1) * psz);
   r->n_digits = (sort->c - 1 + 4) / 5;
+  if (sort->rounds > 0) {
+    const size_t asz = g2 ? sizeof(G2Affine) : sizeof(G1Affine), fsz = asz / 2, pad = 128 * 64;
+    r->round_pts[0] = dev_alloc<unsigned char>((sort->round_max[1] + pad) * asz, &tot);
+    if (sort->rounds > 1) r->round_pts[1] = dev_alloc<unsigned char>((sort->round_max[2] + pad) * asz, &tot);
+    r->round_prefix = dev_alloc<unsigned char>((sort->round_max[1] + pad) * fsz, &tot);
+  }
   NZCP_CUDA(cudaEventCreate(&r->ev_acc0));
   NZCP_CUDA(cudaEventCreate(&r->ev_acc1));
   r->scratch_bytes = tot;
@@ -774,6 +908,9 @@ void msm_run_destroy(MsmRun* r) {
   cudaFree(r->chunk_off);
   cudaFree(r->chunk_partial);
   cudaFree(r->out);
+  cudaFree(r->round_pts[0]);
+  cudaFree(r->round_pts[1]);
+  cudaFree(r->round_prefix);
   if (r->out_host) cudaFreeHost(r->out_host);
   if (r->ev_acc0) cudaEventDestroy(r->ev_acc0);
   if (r->ev_acc1) cudaEventDestroy(r->ev_acc1);
@@ -790,9 +927,35 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
   XYZZ<F>* out = reinterpret_cast<XYZZ<F>*>(r->out);
   NZCP_CUDA(cudaMemsetAsync(r->heavy_count, 0, 2 * sizeof(uint32_t), st));
   NZCP_CUDA(cudaEventRecord(r->ev_acc0, st));
-  msm_accumulate_kernel<F><<<div_up(s->max_tasks, 128), 128, 0, st>>>(reinterpret_cast<const Affine<F>*>(t->pts),
-                                                                     s->entries, s->tasks, s->flags, partial);
-  NZCP_LAUNCH_CHECK();
+  if (s->rounds == 0) {
+    msm_accumulate_kernel<F><<<div_up(s->max_tasks, 128), 128, 0, st>>>(reinterpret_cast<const Affine<F>*>(t->pts),
+                                                                       s->entries, s->tasks, s->flags, partial);
+    NZCP_LAUNCH_CHECK();
+  } else {
+    // pair rounds: table -> pts[0] -> pts[1] -> pts[0]; then the XYZZ accumulation over the last array
+    const Affine<F>* src = reinterpret_cast<const Affine<F>*>(t->pts);
+    for (int rd = 1; rd <= s->rounds; rd++) {
+      Affine<F>* dst = reinterpret_cast<Affine<F>*>(r->round_pts[(rd - 1) & 1]);
+      const uint32_t* off_in = s->round_off + (size_t)(rd - 1) * (nb + 1);
+      const uint32_t* off_out = s->round_off + (size_t)rd * (nb + 1);
+      int k = g_tune_pair_k[rd - 1].load();
+      k = k >= 64 ? 64 : k >= 32 ? 32 : 16;
+      const unsigned grid = div_up(div_up(s->round_max[rd], k), 128);
+      F* scratch = reinterpret_cast<F*>(r->round_prefix);
+#define NZCP_PAIR_LAUNCH(TABLE, KK)                                                                                   \
+      msm_pair_round_kernel<F, TABLE, KK><<<grid, 128, 0, st>>>(src, s->entries, off_in, off_out, nb, dst, scratch)
+      if (rd == 1) {
+        if (k == 64) NZCP_PAIR_LAUNCH(true, 64); else if (k == 32) NZCP_PAIR_LAUNCH(true, 32); else NZCP_PAIR_LAUNCH(true, 16);
+      } else {
+        if (k == 64) NZCP_PAIR_LAUNCH(false, 64); else if (k == 32) NZCP_PAIR_LAUNCH(false, 32); else NZCP_PAIR_LAUNCH(false, 16);
+      }
+#undef NZCP_PAIR_LAUNCH
+      NZCP_LAUNCH_CHECK();
+      src = dst;
+    }
+    msm_accumulate_pts_kernel<F><<<div_up(s->max_tasks, 128), 128, 0, st>>>(src, s->tasks, s->flags, partial);
+    NZCP_LAUNCH_CHECK();
+  }
   NZCP_CUDA(cudaEventRecord(r->ev_acc1, st));
   msm_combine_kernel<F><<<div_up(nb, 128), 128, 0, st>>>(s->task_off, partial, buckets, nb, r->heavy_list,
                                                                      r->heavy_count);

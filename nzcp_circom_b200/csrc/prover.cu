@@ -16,6 +16,7 @@
 
 namespace nzcp {
 
+extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;   // msm.cu
 std::atomic<uint64_t> g_launch_count{0};
 
 static thread_local std::string t_last_error;
@@ -271,8 +272,16 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
   NZCP_CUDA(cudaMalloc(&p->d_wtns, (size_t)zk->n_vars * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_abc, 3 * n * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_h, n * sizeof(Fr)));
-  msm_sort_create(&p->sort_w, zk->n_vars, zk->c_w);
-  msm_sort_create(&p->sort_h, n, zk->c_h);
+  // Pair rounds: the h scalars are dense (512 entries per bucket at n = 2^20): three rounds.  The witness is sparse in
+  // digits (~3.4 non-zero digits per wire, not 16): two rounds at most.
+  int rounds_h = g_tune_rounds_h.load(), rounds_w = g_tune_rounds_w.load();
+  if (rounds_h < 0) rounds_h = msm_pick_rounds(n, zk->c_h);
+  if (rounds_w < 0) {
+    rounds_w = msm_pick_rounds(zk->n_vars, zk->c_w);
+    if (rounds_w > 2) rounds_w = 2;
+  }
+  msm_sort_create(&p->sort_w, zk->n_vars, zk->c_w, rounds_w);
+  msm_sort_create(&p->sort_h, n, zk->c_h, rounds_h);
   msm_run_create(&p->run_a, &p->sort_w, false);
   msm_run_create(&p->run_b1, &p->sort_w, false);
   msm_run_create(&p->run_b2, &p->sort_w, true);

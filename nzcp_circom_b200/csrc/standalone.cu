@@ -4,8 +4,13 @@
 #include <memory>
 
 #include "api_util.cuh"
+#include "msm_pair.cuh"
 
 namespace nzcp {
+
+extern std::atomic<int> g_tune_rounds;                   // msm.cu
+extern std::atomic<int> g_tune_pair_k[kMsmMaxRounds];
+extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;
 
 G1Affine g1_generator();  // synth.cu
 Fr host_fr_root(int k);     // ntt.cu
@@ -51,7 +56,9 @@ __global__ void field_op_kernel(int op, const Fp<P>* a, const Fp<P>* b, Fp<P>* o
     case 2: r = fp_sub(x, y); break;
     case 3: r = fp_mul_portable(x, y); break;
     case 4: r = fp_add_portable(x, y); break;
-    default: r = fp_sub_portable(x, y); break;
+    case 5: r = fp_sub_portable(x, y); break;
+    case 6: r = fp_inv_fast(x); break;                       // safegcd (b ignored)
+    default: r = x.is_zero() ? x : fp_inv(x); break;         // 7: Fermat ladder
   }
   out[i] = r;
 }
@@ -323,13 +330,121 @@ __global__ void __launch_bounds__(256) pipeprobe_kernel(int iters, uint32_t seed
   if (sx == 0x12345678u || sd == 0.123456) sink[0] = sx;
 }
 
+
+// ------------------------------------------------------------------------------------------------ host simulation
+// The MSM data path with the pair rounds, run on the CPU with the SAME __host__ __device__ code the kernels execute
+// (msm_pair.cuh msm_pair_round_body, the signed-digit rule of msm_digits_*_kernel, the round plan of
+// msm_round_plan_kernel restated as plain loops).  Test-only: it lets the no-GPU suite pin the index arithmetic and the
+// special-pair handling of the batched-affine rounds against the oracle; nothing in the product calls it.
+template <class F, int K>
+static void sim_round(bool from_table, const std::vector<Affine<F>>& src, const std::vector<uint32_t>& entries,
+                      const std::vector<uint32_t>& off_in, const std::vector<uint32_t>& off_out, uint32_t nb,
+                      std::vector<Affine<F>>& dst) {
+  const uint32_t n_out = off_out[nb];
+  const uint32_t threads = (n_out + K - 1) / K + 3;   // a few surplus threads, as the over-sized device grid has
+  std::vector<F> scratch((size_t)threads * K);
+  dst.assign(n_out ? n_out : 1, Affine<F>::inf());
+  for (uint32_t t = 0; t < threads; t++) {
+    if (from_table) {
+      PairSource<F, true> ps{src.data(), entries.data()};
+      msm_pair_round_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data());
+    } else {
+      PairSource<F, false> ps{src.data(), nullptr};
+      msm_pair_round_body<F, false, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data());
+    }
+  }
+}
+
+template <class F>
+static XYZZ<F> host_msm_sim(const uint8_t* bases, const uint8_t* scalars, size_t n, int c, int rounds, int k) {
+  const int n_windows = msm_num_windows(c);
+  const uint32_t nb = 1u << (c - 1);
+  std::vector<Affine<F>> table((size_t)n_windows * n + 1);
+  for (size_t i = 0; i < n; i++) {
+    Affine<F> p;
+    memcpy(&p, bases + i * sizeof(Affine<F>), sizeof(Affine<F>));
+    table[i] = p;
+    for (int w = 1; w < n_windows; w++) {
+      if (!p.is_inf()) {
+        XYZZ<F> acc = xyzz_dbl_affine(p);
+        for (int j = 1; j < c; j++) acc = xyzz_dbl(acc);
+        p = xyzz_to_affine(acc);
+      }
+      table[(size_t)w * n + i] = p;
+    }
+  }
+  std::vector<std::vector<uint32_t>> lists(nb);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t sc[8];
+    memcpy(sc, scalars + 32 * i, 32);
+    if (fp_geq_mod<FrParams>(sc)) throw ApiError(NZCP_E_RANGE, "witness/scalar value is not a canonical field element (>= r)");
+    uint32_t carry = 0;
+    for (int w = 0; w < n_windows; w++) {
+      const int pos = w * c;
+      uint32_t d = carry;
+      if (pos < 256) {
+        const int idx = pos >> 5, sh = pos & 31;
+        uint64_t lo = sc[idx], hi = idx + 1 < 8 ? sc[idx + 1] : 0;
+        d += (uint32_t)((lo | (hi << 32)) >> sh) & ((1u << c) - 1);
+      }
+      uint32_t neg = 0;
+      if (d > nb) {
+        d = (1u << c) - d;
+        neg = 1;
+        carry = 1;
+      } else {
+        carry = 0;
+      }
+      if (d) lists[d - 1].push_back(((uint32_t)w * (uint32_t)n + (uint32_t)i) | (neg << 31));
+    }
+  }
+  std::vector<uint32_t> entries;
+  std::vector<std::vector<uint32_t>> off(rounds + 1, std::vector<uint32_t>(nb + 1, 0));
+  for (uint32_t b = 0; b < nb; b++) {
+    uint32_t len = (uint32_t)lists[b].size();
+    entries.insert(entries.end(), lists[b].begin(), lists[b].end());
+    for (int r = 0; r <= rounds; r++) {
+      off[r][b + 1] = off[r][b] + len;
+      len = (len + 1) >> 1;
+    }
+  }
+  entries.push_back(0);
+  std::vector<Affine<F>> cur, nxt;
+  for (int r = 1; r <= rounds; r++) {
+    const std::vector<Affine<F>>& src = r == 1 ? table : cur;
+    switch (k) {
+      case 4: sim_round<F, 4>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
+      case 16: sim_round<F, 16>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
+      case 32: sim_round<F, 32>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
+      case 64: sim_round<F, 64>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
+      default: throw ApiError(NZCP_E_ARG, "additions per thread must be 4, 16, 32 or 64");
+    }
+    cur.swap(nxt);
+  }
+  // XYZZ tail per bucket, then sum_v v * B_v by the running-sum rule
+  XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+  for (uint32_t b = nb; b-- > 0;) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t j = off[rounds][b]; j < off[rounds][b + 1]; j++) {
+      Affine<F> q;
+      bool neg = false;
+      if (rounds == 0) {
+        q = table[entries[j] & 0x7fffffffu];
+        neg = (entries[j] >> 31) != 0;
+      } else {
+        q = cur[j];
+      }
+      if (!q.is_inf()) xyzz_madd(acc, q, neg);
+    }
+    xyzz_add(run, acc);
+    xyzz_add(tot, run);
+  }
+  return tot;
+}
+
 }  // namespace nzcp
 
 using namespace nzcp;
-
-extern "C" {
-
-}  // extern "C"
 
 static void launch_intpipe(int mode, int blocks, int threads, int it, uint32_t seed, uint32_t* sink) {
   switch (mode) {
@@ -514,7 +629,7 @@ int nzcp_selftest(int device, uint64_t seed, uint32_t n_cases, uint32_t* n_bad) 
 int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int device) {
   return api_guard([&] {
     if (!a || !b || !out) throw ApiError(NZCP_E_ARG, "null argument");
-    if (op < 0 || op > 5 || field < 0 || field > 1) throw ApiError(NZCP_E_ARG, "bad op/field");
+    if (op < 0 || op > 7 || field < 0 || field > 1) throw ApiError(NZCP_E_ARG, "bad op/field");
     use_device(device);
     DevBuf da(n * 32), db(n * 32), dout(n * 32);
     NZCP_CUDA(cudaMemcpy(da.p, a, n * 32, cudaMemcpyHostToDevice));
@@ -533,15 +648,17 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
 int nzcp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   return api_guard([&] {
     if (!a || !b || !out) throw ApiError(NZCP_E_ARG, "null argument");
-    if (op < 0 || op > 2 || field < 0 || field > 1) throw ApiError(NZCP_E_ARG, "bad op/field");
+    if (op < 0 || op > 4 || field < 0 || field > 1) throw ApiError(NZCP_E_ARG, "bad op/field");
     for (size_t i = 0; i < n; i++) {
       if (field == 0) {
         Fr x = fp_from_bytes_plain<FrParams>(a + 32 * i), y = fp_from_bytes_plain<FrParams>(b + 32 * i);
-        Fr r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
+        Fr r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : op == 2 ? fp_sub(x, y) : op == 3 ? fp_inv_fast(x)
+               : (x.is_zero() ? x : fp_inv(x));
         fp_to_bytes(r, out + 32 * i);
       } else {
         Fq x = fp_from_bytes_plain<FqParams>(a + 32 * i), y = fp_from_bytes_plain<FqParams>(b + 32 * i);
-        Fq r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
+        Fq r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : op == 2 ? fp_sub(x, y) : op == 3 ? fp_inv_fast(x)
+               : (x.is_zero() ? x : fp_inv(x));
         fp_to_bytes(r, out + 32 * i);
       }
     }
@@ -561,6 +678,30 @@ int nzcp_host_scalar_mul(int g2, const uint8_t* base_mont, const uint8_t* scalar
       if (base_mont) memcpy(&b, base_mont, 64);
       g1_to_plain_bytes(xyzz_mul(G1XYZZ::from_affine(b), k.v), out_plain);
     }
+  });
+}
+
+int nzcp_host_msm_sim(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int g2, int window_bits, int rounds,
+                      int adds_per_thread, uint8_t* out) {
+  return api_guard([&] {
+    if (!out || (n_points && (!bases || !scalars))) throw ApiError(NZCP_E_ARG, "null argument");
+    if (window_bits < 2 || window_bits > 16 || rounds < 0 || rounds > kMsmMaxRounds) throw ApiError(NZCP_E_ARG, "bad window / rounds");
+    if (g2) g2_to_plain_bytes(host_msm_sim<Fq2>(bases, scalars, n_points, window_bits, rounds, adds_per_thread), out);
+    else g1_to_plain_bytes(host_msm_sim<Fq>(bases, scalars, n_points, window_bits, rounds, adds_per_thread), out);
+  });
+}
+
+int nzcp_tuning_set(const char* name, int value) {
+  return api_guard([&] {
+    if (!name) throw ApiError(NZCP_E_ARG, "null argument");
+    const std::string k(name);
+    if (k == "msm_rounds") g_tune_rounds.store(value);
+    else if (k == "prover_rounds_w") g_tune_rounds_w.store(value);
+    else if (k == "prover_rounds_h") g_tune_rounds_h.store(value);
+    else if (k == "pair_k1") g_tune_pair_k[0].store(value);
+    else if (k == "pair_k2") g_tune_pair_k[1].store(value);
+    else if (k == "pair_k3") g_tune_pair_k[2].store(value);
+    else throw ApiError(NZCP_E_ARG, "unknown tuning knob: " + k);
   });
 }
 

@@ -208,3 +208,58 @@ def test_msm_large_linearity(lib):
     ks = {id(P): i + 1 for i, P in enumerate(base_pts)}
     tot = sum(x * ks[id(P)] for x, P in zip(s, pts)) % R
     assert run(s) == fb.mul(tot)
+
+
+@pytest.fixture
+def forced_rounds():
+    """Force the batched-affine pair rounds on (small inputs would run without them) and restore the defaults after."""
+    def force(rounds, k=16):
+        api.tuning_set("msm_rounds", rounds)
+        api.tuning_set("prover_rounds_w", rounds)
+        api.tuning_set("prover_rounds_h", rounds)
+        for name in ("pair_k1", "pair_k2", "pair_k3"):
+            api.tuning_set(name, k)
+    yield force
+    for name, v in (("msm_rounds", -1), ("prover_rounds_w", -1), ("prover_rounds_h", -1), ("pair_k1", 32), ("pair_k2", 32),
+                    ("pair_k3", 32)):
+        api.tuning_set(name, v)
+
+
+@pytest.mark.parametrize("rounds,k", [(1, 16), (2, 16), (3, 16), (3, 32), (2, 64)])
+@pytest.mark.parametrize("g2", [False, True])
+def test_msm_pair_rounds_forced_edge_cases(lib, fixed_bases, forced_rounds, g2, rounds, k):
+    """The edge-case MSMs again with the pair rounds forced on: equal points (tangent pairs), opposite points (infinity
+    results carried into the next round), infinity bases, witness-like scalars, several window sizes."""
+    forced_rounds(rounds, k)
+    rng = random.Random(177 + g2 + rounds)
+    fb = fixed_bases[g2]
+    curve = ob.G2 if g2 else ob.G1
+    P = fb.mul(5)
+    pts = [P, P, curve.neg(P), None, fb.mul(9), None, P, fb.mul(11)] + _rand_points(None, fb, rng, 120)
+    scalars = [3, 3, 3, 7, 0, 0, R - 1, 1] + [rng.choice([0, 1, 1, rng.randrange(256), rng.randrange(R)])
+                                               for _ in range(120)]
+    for c in (0, 2, 5):
+        _msm_case(g2, pts, scalars, window_bits=c)
+    _msm_case(g2, [P] * 64, [1] * 64, window_bits=3)
+    _msm_case(g2, [P] * 61, [R - 1] * 61, window_bits=4)
+    _msm_case(g2, [P, curve.neg(P)] * 8, [12345] * 16, window_bits=3)
+    _msm_case(g2, [None] * 10, [rng.randrange(R) for _ in range(10)])
+    _msm_case(g2, [], [])
+    _msm_case(g2, [P], [R - 1])
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3])
+def test_msm_pair_rounds_forced_mid_size(lib, forced_rounds, rounds):
+    """2^13 points, witness-like scalars (heavy bucket "1"), vs the C oracle, every round count."""
+    from oracle import cref
+    forced_rounds(rounds, 32)
+    n = 1 << 13
+    bases = bytes(api.synth_points(9, n))
+    rng = random.Random(12)
+    sc = [rng.choice([0, 1, 1, 1, rng.randrange(256), rng.randrange(R)]) for _ in range(n)]
+    scb = b"".join(le32(x) for x in sc)
+    got, _ = api.msm(bases, scb, n)
+    assert got == cref.msm(bases, scb, n, False, 4)
+    b2 = bytes(api.synth_points(10, 2048, g2=True))
+    got2, _ = api.msm(b2, scb[:2048 * 32], 2048, g2=True)
+    assert got2 == cref.msm(b2, scb[:2048 * 32], 2048, True, 4)

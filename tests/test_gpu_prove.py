@@ -283,3 +283,25 @@ def test_two_devices_in_one_process(lib):
     assert outs[0]["proof"] == outs[1]["proof"] and outs[0]["h"] == outs[1]["h"]
     exp, _ = oprover.prove(formats.read_zkey(c["zkey_bytes"]), c["witness"], 9, 10)
     assert outs[1]["proof"] == oprover.proof_to_bytes(exp)
+
+
+@pytest.mark.parametrize("rounds", [1, 3])
+def test_prove_with_pair_rounds_forced(lib, rounds):
+    """A small proof with the batched-affine pair rounds forced on in all five MSMs: still bit-exact vs the oracle."""
+    names = ("msm_rounds", "prover_rounds_w", "prover_rounds_h")
+    try:
+        for nm in names:
+            api.tuning_set(nm, rounds)
+        c = tiny_case(31 + rounds, 700, 13, 30)
+        zkd = formats.read_zkey(c["zkey_bytes"])
+        exp, pub, parts = oprover.prove(zkd, c["witness"], 77, 99, return_parts=True)
+        with api.Zkey(c["zkey_bytes"]) as zk, api.Prover(zk) as pr:
+            got = pr.prove(c["wtns_bytes"], r=77, s=99, debug=True)
+        assert got["msm_a"] == g1_plain_bytes(parts["A"])
+        assert got["msm_b2"] == g2_plain_bytes(parts["B2"])
+        assert got["msm_c"] == g1_plain_bytes(parts["C"])
+        assert got["msm_h"] == g1_plain_bytes(parts["H"])
+        assert got["proof"] == oprover.proof_to_bytes(exp)
+    finally:
+        for nm in names:
+            api.tuning_set(nm, -1)
