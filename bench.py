@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--provers", type=int, default=4, help="concurrent provers (host threads + stream sets) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
+                    help="library tuning knob (include/nzcp_prover.h nzcp_tuning_set), e.g. prover_rounds_h=0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,6 +194,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
+    for kv in args.tune:
+        k, v = kv.split("=")
+        api.tuning_set(k, int(v))
     zkey, wtns, dims = make_workload(args.shape, local, B, 1 + rank * B)
     zk = api.Zkey(zkey, device=local)
     pool = api.ProverPool(zk, args.provers)
@@ -284,6 +289,8 @@ def main():
             "p50_latency_ms": 1e3 * statistics.median(lat) if lat else None,
             "gpu_launches": launches, "clocks": clocks, "stage_ms": dbg["stage_ms"],
         }
+        if args.tune:
+            line["config"]["tune"] = args.tune
         line.update(roofline_block(dbg, zk, hbm, peak_src))
         if not args.no_cpu_baseline:
             times, stages, thr, cproof = cpu_reference_proofs(zkey, wtns, 1)
