@@ -142,7 +142,7 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
 /* Tuning knobs for experiments and tests (process-wide, read when a plan is created / a run is launched):
  *   "msm_rounds"  batched-affine pair rounds per MSM: -1 = automatic (by size), 0..3 forced
  *   "prover_rounds_w" / "prover_rounds_h"  the same for a prover's witness MSMs / H MSM (read by nzcp_prover_create)
- *   "pair_k1" / "pair_k2" / "pair_k3"  additions sharing one inversion per thread in round 1 / 2 / 3: 16, 32 or 64 */
+ *   "pair_k1" / "pair_k2" / "pair_k3"  additions per thread in round 1 / 2 / 3: 4, 8, 16 or 32 */
 int nzcp_tuning_set(const char* name, int value);
 
 /* Integer-pipe microbenchmark (the MSM / NTT roofline denominator): out[0] = IMAD.WIDE.U32 (32x32->64 multiply-add) per
@@ -161,7 +161,7 @@ int nzcp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, ui
 /* k * base (Montgomery affine base as in the zkey, NULL = the group generator); out = plain affine. */
 int nzcp_host_scalar_mul(int g2, const uint8_t* base_mont, const uint8_t* scalar, uint8_t* out_plain);
 /* The MSM data path INCLUDING the batched-affine pair rounds of csrc/msm_pair.cuh, executed on the CPU with the same
- * __host__ __device__ code the kernels run (rounds = 0..3 pair rounds, adds_per_thread = 4, 16, 32 or 64).  Lets the
+ * __host__ __device__ code the kernels run (rounds = 0..3 pair rounds, adds_per_thread = 4, 8, 16 or 32).  Lets the
  * no-GPU suite check the rounds' index arithmetic and special-pair handling against the oracle.  out = plain affine. */
 int nzcp_host_msm_sim(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int g2, int window_bits, int rounds,
                       int adds_per_thread, uint8_t* out);

@@ -139,6 +139,7 @@ struct MsmRun {
   cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;  // around the bucket accumulation (pair rounds + XYZZ kernel)
   void* round_pts[2] = {nullptr, nullptr};   // affine point arrays of the pair rounds (ping-pong)
   void* round_prefix = nullptr;              // prefix products of the shared inversion, [step][thread]
+  void* round_prod = nullptr;                // per-thread denominator products, inverted in place between the passes
   size_t scratch_bytes = 0;
 };
 void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2);

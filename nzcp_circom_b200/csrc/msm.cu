@@ -481,15 +481,35 @@ msm_accumulate_pts_kernel(const Affine<F>* __restrict__ pts, const uint2* __rest
   partial[t] = acc;
 }
 
-// One pair round (msm_pair.cuh): thread t produces K consecutive points of the round.
+// One pair round (msm_pair.cuh) = forward, invert, backward; thread t of forward / backward owns K consecutive points of
+// the round, thread g of invert owns 32 consecutive thread products.
+static constexpr int kPairInvGroup = 32;
 template <class F, bool FROM_TABLE, int K>
 __global__ void __launch_bounds__(128)
-msm_pair_round_kernel(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
-                      const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t n_buckets,
-                      Affine<F>* __restrict__ dst, F* __restrict__ scratch) {
+msm_pair_forward_kernel(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
+                        const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t n_buckets,
+                        F* __restrict__ scratch, F* __restrict__ prod) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   PairSource<F, FROM_TABLE> ps{src, entries};
-  msm_pair_round_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, dst, scratch);
+  msm_pair_forward_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, scratch, prod);
+}
+
+template <class F, int K>
+__global__ void __launch_bounds__(64)
+msm_pair_invert_kernel(F* __restrict__ prod, const uint32_t* __restrict__ off_out, uint32_t n_buckets) {
+  const uint32_t n_out = off_out[n_buckets];
+  const uint32_t n_prod = (n_out + K - 1) / K;      // threads of the forward kernel that had work
+  msm_pair_invert_body<F, kPairInvGroup>(blockIdx.x * blockDim.x + threadIdx.x, prod, n_prod);
+}
+
+template <class F, bool FROM_TABLE, int K>
+__global__ void __launch_bounds__(128)
+msm_pair_backward_kernel(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
+                         const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t n_buckets,
+                         Affine<F>* __restrict__ dst, const F* __restrict__ scratch, const F* __restrict__ inv_prod) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  PairSource<F, FROM_TABLE> ps{src, entries};
+  msm_pair_backward_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, dst, scratch, inv_prod);
 }
 
 template <class T>
@@ -696,19 +716,20 @@ int msm_num_windows(int c) {
 // Tuning knobs (nzcp_tuning_set): pair rounds per MSM (-1 = msm_pick_rounds) and additions per thread in round 1, 2, 3.
 std::atomic<int> g_tune_rounds{-1};
 std::atomic<int> g_tune_rounds_w{-1}, g_tune_rounds_h{-1};   // prover: witness MSMs / H MSM (-1 = default)
-std::atomic<int> g_tune_pair_k[kMsmMaxRounds] = {{32}, {32}, {32}};
+std::atomic<int> g_tune_pair_k[kMsmMaxRounds] = {{16}, {16}, {16}};
 
-// Pair rounds pay when the buckets are long: every round costs a launch and leaves ceil(len / 2) points per bucket,
-// and the XYZZ tail wants >= ~16 points per bucket to keep its threads busy.
+// Pair rounds are OFF unless asked for (nzcp_tuning_set "msm_rounds" / "prover_rounds_*").  Measured on the B200
+// (profiles/r02_pair_rounds.md): they cut the executed products of the H accumulation by a third, but an affine
+// addition needs each operand twice (denominator pass, then the addition itself) and round 1 gathers its operands
+// from the 1 GB window table -- random 128-byte lines come in at ~3.7 TB/s, so round 1 alone costs what the XYZZ kernel
+// needs for the same additions with its single gather hidden under the multiplies (H: 3.1 ms with rounds vs 2.75 ms
+// without; whole-proof throughput +2..3 % at +5 GB of scratch per prover).
 int msm_pick_rounds(size_t n_points, int c) {
+  (void)n_points;
+  (void)c;
   const int forced = g_tune_rounds.load();
   if (forced >= 0) return forced > kMsmMaxRounds ? kMsmMaxRounds : forced;
-  const size_t entries = (size_t)msm_num_windows(c) * n_points;
-  if (entries < ((size_t)1 << 21)) return 0;
-  const size_t per_bucket = entries >> (c - 1);
-  int r = 0;
-  while (r < kMsmMaxRounds && (per_bucket >> (r + 1)) >= 32) r++;
-  return r;
+  return 0;
 }
 
 template <class T>
@@ -893,6 +914,7 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
     r->round_pts[0] = dev_alloc<unsigned char>((sort->round_max[1] + pad) * asz, &tot);
     if (sort->rounds > 1) r->round_pts[1] = dev_alloc<unsigned char>((sort->round_max[2] + pad) * asz, &tot);
     r->round_prefix = dev_alloc<unsigned char>((sort->round_max[1] + pad) * fsz, &tot);
+    r->round_prod = dev_alloc<unsigned char>((sort->round_max[1] / 4 + pad) * fsz, &tot);   // >= 4 additions per thread
   }
   NZCP_CUDA(cudaEventCreate(&r->ev_acc0));
   NZCP_CUDA(cudaEventCreate(&r->ev_acc1));
@@ -911,6 +933,7 @@ void msm_run_destroy(MsmRun* r) {
   cudaFree(r->round_pts[0]);
   cudaFree(r->round_pts[1]);
   cudaFree(r->round_prefix);
+  cudaFree(r->round_prod);
   if (r->out_host) cudaFreeHost(r->out_host);
   if (r->ev_acc0) cudaEventDestroy(r->ev_acc0);
   if (r->ev_acc1) cudaEventDestroy(r->ev_acc1);
@@ -939,18 +962,29 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
       const uint32_t* off_in = s->round_off + (size_t)(rd - 1) * (nb + 1);
       const uint32_t* off_out = s->round_off + (size_t)rd * (nb + 1);
       int k = g_tune_pair_k[rd - 1].load();
-      k = k >= 64 ? 64 : k >= 32 ? 32 : 16;
+      k = k >= 32 ? 32 : k >= 16 ? 16 : k >= 8 ? 8 : 4;
       const unsigned grid = div_up(div_up(s->round_max[rd], k), 128);
+      const unsigned grid_inv = div_up(div_up((size_t)grid * 128, kPairInvGroup), 64);
       F* scratch = reinterpret_cast<F*>(r->round_prefix);
-#define NZCP_PAIR_LAUNCH(TABLE, KK)                                                                                   \
-      msm_pair_round_kernel<F, TABLE, KK><<<grid, 128, 0, st>>>(src, s->entries, off_in, off_out, nb, dst, scratch)
+      F* prod = reinterpret_cast<F*>(r->round_prod);
+#define NZCP_PAIR_LAUNCH(TABLE, KK)                                                                                       \
+      do {                                                                                                                \
+        msm_pair_forward_kernel<F, TABLE, KK><<<grid, 128, 0, st>>>(src, s->entries, off_in, off_out, nb, scratch, prod); \
+        NZCP_LAUNCH_CHECK();                                                                                              \
+        msm_pair_invert_kernel<F, KK><<<grid_inv, 64, 0, st>>>(prod, off_out, nb);                                        \
+        NZCP_LAUNCH_CHECK();                                                                                              \
+        msm_pair_backward_kernel<F, TABLE, KK><<<grid, 128, 0, st>>>(src, s->entries, off_in, off_out, nb, dst, scratch,  \
+                                                                     prod);                                               \
+        NZCP_LAUNCH_CHECK();                                                                                              \
+      } while (0)
       if (rd == 1) {
-        if (k == 64) NZCP_PAIR_LAUNCH(true, 64); else if (k == 32) NZCP_PAIR_LAUNCH(true, 32); else NZCP_PAIR_LAUNCH(true, 16);
+        if (k == 32) NZCP_PAIR_LAUNCH(true, 32); else if (k == 16) NZCP_PAIR_LAUNCH(true, 16);
+        else if (k == 8) NZCP_PAIR_LAUNCH(true, 8); else NZCP_PAIR_LAUNCH(true, 4);
       } else {
-        if (k == 64) NZCP_PAIR_LAUNCH(false, 64); else if (k == 32) NZCP_PAIR_LAUNCH(false, 32); else NZCP_PAIR_LAUNCH(false, 16);
+        if (k == 32) NZCP_PAIR_LAUNCH(false, 32); else if (k == 16) NZCP_PAIR_LAUNCH(false, 16);
+        else if (k == 8) NZCP_PAIR_LAUNCH(false, 8); else NZCP_PAIR_LAUNCH(false, 4);
       }
 #undef NZCP_PAIR_LAUNCH
-      NZCP_LAUNCH_CHECK();
       src = dst;
     }
     msm_accumulate_pts_kernel<F><<<div_up(s->max_tasks, 128), 128, 0, st>>>(src, s->tasks, s->flags, partial);

@@ -4,12 +4,17 @@
 // After the bucket sort every bucket owns a contiguous list of points.  One round replaces each list by the sums of its
 // adjacent pairs (an odd last point is copied): len -> ceil(len / 2).  The additions are AFFINE,
 //     lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1,
-// and the K additions of one thread share ONE field inversion (Montgomery's trick): a forward pass multiplies the
-// denominators into a running product (1 product per addition; the running products go to a scratch array), the
-// product is inverted once by division steps (fp_inv_fast, ~50 products), and a backward pass peels the individual
-// inverses off (2 products) and finishes the additions (3 products): 6 + 50 / K field products per addition instead of
-// the 10 of an XYZZ mixed addition (SURVEY.md 8d canonical count).  Group elements are exact, so the MSM result is
-// bit-identical whichever way its terms were associated.
+// and the additions share their field inversions (Montgomery's trick, two levels).  A round is three kernels:
+//   forward   thread t multiplies the denominators of its K pairs into a running product (1 product per addition; the
+//             running products go to a scratch array) and publishes the total P_t;
+//   invert    the P_t are inverted 32 at a time: prefix products, ONE inversion by division steps (fp_inv_fast, ~50
+//             products' worth of issue slots, constant time), back-substitution: 3 + 50/32 products per P_t;
+//   backward  thread t peels the individual inverses off 1 / P_t (2 products per addition) and finishes the additions
+//             (3 products).
+// 6 + ~5 / K field products per addition instead of the 10 of an XYZZ mixed addition (SURVEY.md 8d canonical count),
+// and the two hot kernels are short threads of plain Montgomery products -- the long serial inversion sits in a small
+// kernel of its own.  Group elements are exact, so the MSM result is bit-identical whichever way its terms were
+// associated.
 //
 // Special pairs never enter the shared product (their denominator is replaced by "skip"):
 //   P + infinity, infinity + P -> the other point;  P + (-P) -> infinity;  P + P -> tangent: the denominator is 2 y
@@ -27,19 +32,54 @@ template <class F, bool FROM_TABLE>
 struct PairSource {
   const Affine<F>* pts;
   const uint32_t* entries;
-  HD F x(uint32_t idx) const {
-    if (FROM_TABLE) idx = entries[idx] & 0x7fffffffu;
-    return pts[idx].x;
-  }
-  HD Affine<F> point(uint32_t idx) const {
+  HD uint32_t slot(uint32_t idx) const { return FROM_TABLE ? entries[idx] : idx; }   // table index | sign, or the index
+  HD F x_at(uint32_t slot) const { return pts[FROM_TABLE ? (slot & 0x7fffffffu) : slot].x; }
+  HD Affine<F> point_at(uint32_t slot) const {
     if (FROM_TABLE) {
-      const uint32_t e = entries[idx];
-      Affine<F> p = pts[e & 0x7fffffffu];
-      if (e >> 31) p.y = f_neg(p.y);
+      Affine<F> p = pts[slot & 0x7fffffffu];
+      if (slot >> 31) p.y = f_neg(p.y);
       return p;
     }
-    return pts[idx];
+    return pts[slot];
   }
+  HD Affine<F> point(uint32_t idx) const { return point_at(slot(idx)); }
+  // Ask for the point's cache line ahead of its use (device only; the gathers of round 1 miss L2 four times out of five).
+  HD void prefetch(uint32_t slot, bool whole_point) const {
+#if defined(__CUDA_ARCH__)
+    // 64-byte granules (the points are 64-byte aligned): G1 x or whole point = 1, G2 x = 1, G2 whole point = 2
+    const char* a = reinterpret_cast<const char*>(pts + (FROM_TABLE ? (slot & 0x7fffffffu) : slot));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    if (sizeof(F) > 32 && whole_point) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 64));
+#else
+    (void)slot;
+    (void)whole_point;
+#endif
+  }
+};
+
+// Position of an output slot inside the bucket structure: walks forward / backward over the (possibly empty) buckets.
+struct PairWalk {
+  const uint32_t* off_in;
+  const uint32_t* off_out;
+  uint32_t s, out0, out1, in0, len;
+  HD void load() {
+    out0 = off_out[s];
+    out1 = off_out[s + 1];
+    in0 = off_in[s];
+    len = off_in[s + 1] - in0;
+  }
+  HD void forward_to(uint32_t o) {   // o >= out0
+    if (o < out1) return;
+    do s++; while (o >= off_out[s + 1]);
+    load();
+  }
+  HD void backward_to(uint32_t o) {  // o < out1
+    if (o >= out0) return;
+    do s--; while (o < off_out[s]);
+    load();
+  }
+  HD uint32_t first(uint32_t o) const { return in0 + 2 * (o - out0); }       // input slot of the pair's first point
+  HD bool paired(uint32_t o) const { return 2 * (o - out0) + 1 < len; }      // false: odd point out, copied
 };
 
 // Kind of the pair and, for the two kinds that need an inversion, its denominator.
@@ -58,43 +98,59 @@ HD int pair_classify(const Affine<F>& p1, const Affine<F>& p2, F& den) {
   return kPairNormal;
 }
 
-// One thread of a pair round: outputs [t * K, t * K + K) of the round.  off_in / off_out: bucket offsets (n_buckets + 1
-// entries) of the input and output point arrays; scratch: K x stride running products, element (i, t) at i * stride + t.
-template <class F, bool FROM_TABLE, int K>
-HD void msm_pair_round_body(uint32_t t, uint32_t stride, const PairSource<F, FROM_TABLE>& src, const uint32_t* off_in,
-                            const uint32_t* off_out, uint32_t n_buckets, Affine<F>* dst, F* scratch) {
+// The pairs of thread t: outputs [t * K, t * K + K) of the round.
+template <int K>
+HD bool pair_thread_range(uint32_t t, const uint32_t* off_out, uint32_t n_buckets, uint32_t& o0, uint32_t& cnt) {
   const uint32_t n_out = off_out[n_buckets];
-  if ((uint64_t)t * K >= n_out) return;
-  const uint32_t o0 = t * K;
-  const uint32_t cnt = n_out - o0 < (uint32_t)K ? n_out - o0 : (uint32_t)K;
-  uint32_t s;
-  {
-    uint32_t lo = 0, hi = n_buckets;   // off_out[lo] <= o0 < off_out[hi]
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (off_out[mid] <= o0) lo = mid; else hi = mid;
-    }
-    s = lo;
+  if ((uint64_t)t * K >= n_out) return false;
+  o0 = t * K;
+  cnt = n_out - o0 < (uint32_t)K ? n_out - o0 : (uint32_t)K;
+  return true;
+}
+HD void pair_walk_seek(PairWalk& wk, uint32_t o, uint32_t n_buckets) {
+  uint32_t lo = 0, hi = n_buckets;   // off_out[lo] <= o < off_out[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (wk.off_out[mid] <= o) lo = mid; else hi = mid;
   }
-  uint32_t seg_out0 = off_out[s], seg_out1 = off_out[s + 1], seg_in0 = off_in[s], seg_len = off_in[s + 1] - seg_in0;
+  wk.s = lo;
+  wk.load();
+}
+
+// Forward kernel body.  off_in / off_out: bucket offsets (n_buckets + 1 entries) of the input and output point arrays;
+// scratch: K x stride running products, element (i, t) at i * stride + t; prod[t] = product of the thread's denominators
+// (one() when it has none).  Runs one step ahead of itself: while pair i is multiplied the lines of pair i + 1 are on
+// their way to L1.
+template <class F, bool FROM_TABLE, int K>
+HD void msm_pair_forward_body(uint32_t t, uint32_t stride, const PairSource<F, FROM_TABLE>& src, const uint32_t* off_in,
+                              const uint32_t* off_out, uint32_t n_buckets, F* scratch, F* prod) {
+  uint32_t o0, cnt;
+  if (!pair_thread_range<K>(t, off_out, n_buckets, o0, cnt)) return;
+  PairWalk wk{off_in, off_out, 0, 0, 0, 0, 0};
+  pair_walk_seek(wk, o0, n_buckets);
   F pre = F::one();
   bool have = false;
+  bool pair_cur = wk.paired(o0);
+  uint32_t a_cur = src.slot(wk.first(o0)), b_cur = pair_cur ? src.slot(wk.first(o0) + 1) : 0;
   for (uint32_t i = 0; i < cnt; i++) {
-    const uint32_t o = o0 + i;
-    while (o >= seg_out1) {   // next non-empty bucket
-      s++;
-      seg_out0 = seg_out1;
-      seg_out1 = off_out[s + 1];
-      seg_in0 = off_in[s];
-      seg_len = off_in[s + 1] - seg_in0;
+    bool pair_nxt = false;
+    uint32_t a_nxt = 0, b_nxt = 0;
+    if (i + 1 < cnt) {
+      wk.forward_to(o0 + i + 1);
+      pair_nxt = wk.paired(o0 + i + 1);
+      if (pair_nxt) {
+        a_nxt = src.slot(wk.first(o0 + i + 1));
+        b_nxt = src.slot(wk.first(o0 + i + 1) + 1);
+        src.prefetch(a_nxt, false);
+        src.prefetch(b_nxt, false);
+      }
     }
-    const uint32_t j = o - seg_out0, i0 = seg_in0 + 2 * j;
-    if (2 * j + 1 < seg_len) {
-      const F x1 = src.x(i0), x2 = src.x(i0 + 1);
+    if (pair_cur) {
+      const F x1 = src.x_at(a_cur), x2 = src.x_at(b_cur);
       F den = f_sub(x2, x1);
       bool use = true;
       if (den.is_zero() || x1.is_zero() || x2.is_zero()) {   // rare: look at the whole points
-        const int kind = pair_classify(src.point(i0), src.point(i0 + 1), den);
+        const int kind = pair_classify(src.point_at(a_cur), src.point_at(b_cur), den);
         use = kind == kPairNormal || kind == kPairDouble;
       }
       if (use) {
@@ -103,43 +159,96 @@ HD void msm_pair_round_body(uint32_t t, uint32_t stride, const PairSource<F, FRO
       }
     }
     scratch[(size_t)i * stride + t] = pre;
+    pair_cur = pair_nxt;
+    a_cur = a_nxt;
+    b_cur = b_nxt;
   }
-  F inv = have ? f_inv_fast(pre) : F::one();
+  prod[t] = pre;
+}
+
+// Invert kernel body: v[g * KI .. g * KI + KI) <- their inverses, one inversion for the group.  No element is zero
+// (denominators of special pairs never enter a product).
+template <class F, int KI>
+HD void msm_pair_invert_body(uint32_t g, F* v, uint32_t n) {
+  const uint32_t b = g * KI;
+  if (b >= n) return;
+  const uint32_t cnt = n - b < (uint32_t)KI ? n - b : (uint32_t)KI;
+  F pre[KI];
+  F run = v[b];
+  pre[0] = run;
+  for (uint32_t i = 1; i < cnt; i++) {
+    run = f_mul(run, v[b + i]);
+    pre[i] = run;
+  }
+  F inv = f_inv_fast(run);
+  for (uint32_t i = cnt; i-- > 1;) {
+    const F x = v[b + i];
+    v[b + i] = f_mul(inv, pre[i - 1]);
+    inv = f_mul(inv, x);
+  }
+  v[b] = inv;
+}
+
+// Backward kernel body: inv_prod[t] = 1 / prod[t].
+template <class F, bool FROM_TABLE, int K>
+HD void msm_pair_backward_body(uint32_t t, uint32_t stride, const PairSource<F, FROM_TABLE>& src, const uint32_t* off_in,
+                               const uint32_t* off_out, uint32_t n_buckets, Affine<F>* dst, const F* scratch,
+                               const F* inv_prod) {
+  uint32_t o0, cnt;
+  if (!pair_thread_range<K>(t, off_out, n_buckets, o0, cnt)) return;
+  PairWalk wk{off_in, off_out, 0, 0, 0, 0, 0};
+  pair_walk_seek(wk, o0 + cnt - 1, n_buckets);
+  F inv = inv_prod[t];
+  bool pair_cur;
+  uint32_t a_cur, b_cur;
+  {
+    const uint32_t o = o0 + cnt - 1;
+    pair_cur = wk.paired(o);
+    a_cur = src.slot(wk.first(o));
+    b_cur = pair_cur ? src.slot(wk.first(o) + 1) : 0;
+  }
   for (uint32_t i = cnt; i-- > 0;) {
     const uint32_t o = o0 + i;
-    while (o < seg_out0) {    // previous non-empty bucket
-      s--;
-      seg_out1 = seg_out0;
-      seg_out0 = off_out[s];
-      seg_in0 = off_in[s];
-      seg_len = off_in[s + 1] - seg_in0;
+    bool pair_nxt = false;
+    uint32_t a_nxt = 0, b_nxt = 0;
+    if (i > 0) {
+      wk.backward_to(o - 1);
+      pair_nxt = wk.paired(o - 1);
+      a_nxt = src.slot(wk.first(o - 1));
+      src.prefetch(a_nxt, true);
+      if (pair_nxt) {
+        b_nxt = src.slot(wk.first(o - 1) + 1);
+        src.prefetch(b_nxt, true);
+      }
     }
-    const uint32_t j = o - seg_out0, i0 = seg_in0 + 2 * j;
-    if (2 * j + 1 >= seg_len) {     // odd point out: carried to the next round as it is
-      dst[o] = src.point(i0);
-      continue;
-    }
-    const Affine<F> p1 = src.point(i0), p2 = src.point(i0 + 1);
-    F den;
-    const int kind = pair_classify(p1, p2, den);
-    if (kind >= kPairFirst) {
-      dst[o] = kind == kPairFirst ? p1 : kind == kPairSecond ? p2 : Affine<F>::inf();
-      continue;
-    }
-    const F before = i ? scratch[(size_t)(i - 1) * stride + t] : F::one();   // product of the denominators before this one
-    const F dinv = f_mul(inv, before);
-    inv = f_mul(inv, den);
-    F num;
-    if (kind == kPairDouble) {
-      const F xx = f_sqr(p1.x);
-      num = f_add(f_dbl(xx), xx);
+    if (!pair_cur) {     // odd point out: carried to the next round as it is
+      dst[o] = src.point_at(a_cur);
     } else {
-      num = f_sub(p2.y, p1.y);
+      const Affine<F> p1 = src.point_at(a_cur), p2 = src.point_at(b_cur);
+      F den;
+      const int kind = pair_classify(p1, p2, den);
+      if (kind >= kPairFirst) {
+        dst[o] = kind == kPairFirst ? p1 : kind == kPairSecond ? p2 : Affine<F>::inf();
+      } else {
+        const F before = i ? scratch[(size_t)(i - 1) * stride + t] : F::one();   // product of the denominators before this one
+        const F dinv = f_mul(inv, before);
+        inv = f_mul(inv, den);
+        F num;
+        if (kind == kPairDouble) {
+          const F xx = f_sqr(p1.x);
+          num = f_add(f_dbl(xx), xx);
+        } else {
+          num = f_sub(p2.y, p1.y);
+        }
+        const F lam = f_mul(num, dinv);
+        const F x3 = f_sub(f_sub(f_sqr(lam), p1.x), p2.x);
+        const F y3 = f_sub(f_mul(lam, f_sub(p1.x, x3)), p1.y);
+        dst[o] = Affine<F>{x3, y3};
+      }
     }
-    const F lam = f_mul(num, dinv);
-    const F x3 = f_sub(f_sub(f_sqr(lam), p1.x), p2.x);
-    const F y3 = f_sub(f_mul(lam, f_sub(p1.x, x3)), p1.y);
-    dst[o] = Affine<F>{x3, y3};
+    pair_cur = pair_nxt;
+    a_cur = a_nxt;
+    b_cur = b_nxt;
   }
 }
 

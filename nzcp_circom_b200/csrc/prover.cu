@@ -272,14 +272,10 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
   NZCP_CUDA(cudaMalloc(&p->d_wtns, (size_t)zk->n_vars * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_abc, 3 * n * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_h, n * sizeof(Fr)));
-  // Pair rounds: the h scalars are dense (512 entries per bucket at n = 2^20): three rounds.  The witness is sparse in
-  // digits (~3.4 non-zero digits per wire, not 16): two rounds at most.
+  // Batched-affine pair rounds (msm_pair.cuh) are an opt-in: see msm_pick_rounds for the measurement behind the default.
   int rounds_h = g_tune_rounds_h.load(), rounds_w = g_tune_rounds_w.load();
   if (rounds_h < 0) rounds_h = msm_pick_rounds(n, zk->c_h);
-  if (rounds_w < 0) {
-    rounds_w = msm_pick_rounds(zk->n_vars, zk->c_w);
-    if (rounds_w > 2) rounds_w = 2;
-  }
+  if (rounds_w < 0) rounds_w = msm_pick_rounds(zk->n_vars, zk->c_w);
   msm_sort_create(&p->sort_w, zk->n_vars, zk->c_w, rounds_w);
   msm_sort_create(&p->sort_h, n, zk->c_h, rounds_h);
   msm_run_create(&p->run_a, &p->sort_w, false);

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) pipeprobe_kernel(int iters, uint32_t seed
 
 // ------------------------------------------------------------------------------------------------ host simulation
 // The MSM data path with the pair rounds, run on the CPU with the SAME __host__ __device__ code the kernels execute
-// (msm_pair.cuh msm_pair_round_body, the signed-digit rule of msm_digits_*_kernel, the round plan of
+// (msm_pair.cuh forward / invert / backward bodies, the signed-digit rule of msm_digits_*_kernel, the round plan of
 // msm_round_plan_kernel restated as plain loops).  Test-only: it lets the no-GPU suite pin the index arithmetic and the
 // special-pair handling of the batched-affine rounds against the oracle; nothing in the product calls it.
 template <class F, int K>
@@ -342,15 +342,24 @@ static void sim_round(bool from_table, const std::vector<Affine<F>>& src, const 
                       std::vector<Affine<F>>& dst) {
   const uint32_t n_out = off_out[nb];
   const uint32_t threads = (n_out + K - 1) / K + 3;   // a few surplus threads, as the over-sized device grid has
-  std::vector<F> scratch((size_t)threads * K);
+  std::vector<F> scratch((size_t)threads * K), prod(threads + 40, F::one());
   dst.assign(n_out ? n_out : 1, Affine<F>::inf());
-  for (uint32_t t = 0; t < threads; t++) {
-    if (from_table) {
-      PairSource<F, true> ps{src.data(), entries.data()};
-      msm_pair_round_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data());
-    } else {
-      PairSource<F, false> ps{src.data(), nullptr};
-      msm_pair_round_body<F, false, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data());
+  const uint32_t n_prod = (n_out + K - 1) / K;
+  for (int phase = 0; phase < 3; phase++) {
+    if (phase == 1) {
+      for (uint32_t g = 0; g * 32 < n_prod + 64; g++) msm_pair_invert_body<F, 32>(g, prod.data(), n_prod);
+      continue;
+    }
+    for (uint32_t t = 0; t < threads; t++) {
+      if (from_table) {
+        PairSource<F, true> ps{src.data(), entries.data()};
+        if (phase == 0) msm_pair_forward_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, scratch.data(), prod.data());
+        else msm_pair_backward_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data(), prod.data());
+      } else {
+        PairSource<F, false> ps{src.data(), nullptr};
+        if (phase == 0) msm_pair_forward_body<F, false, K>(t, threads, ps, off_in.data(), off_out.data(), nb, scratch.data(), prod.data());
+        else msm_pair_backward_body<F, false, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data(), prod.data());
+      }
     }
   }
 }
@@ -416,8 +425,8 @@ static XYZZ<F> host_msm_sim(const uint8_t* bases, const uint8_t* scalars, size_t
       case 4: sim_round<F, 4>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
       case 16: sim_round<F, 16>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
       case 32: sim_round<F, 32>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
-      case 64: sim_round<F, 64>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
-      default: throw ApiError(NZCP_E_ARG, "additions per thread must be 4, 16, 32 or 64");
+      case 8: sim_round<F, 8>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
+      default: throw ApiError(NZCP_E_ARG, "additions per thread must be 4, 8, 16 or 32");
     }
     cur.swap(nxt);
   }

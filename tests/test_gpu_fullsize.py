@@ -98,3 +98,18 @@ def test_msm_dense_full_size_vs_c_oracle(lib, g2, log_n):
     sc[1, 0] = 1
     got, _ = api.msm(bases, sc, n, g2=g2)
     assert got == cref.msm(bases, sc, n, g2, cref.max_threads())
+
+
+@pytest.mark.parametrize("rounds", [3])
+def test_msm_dense_full_size_with_pair_rounds(lib, rounds):
+    """The opt-in batched-affine pair rounds at 2^20 dense points (8.4 M + 4.2 M + 2.1 M affine additions sharing
+    inversions, then the XYZZ tail) against the C oracle."""
+    n = 1 << 20
+    bases = bytes(api.synth_points(77, n))
+    sc = _rand_fr_mont(n, 1234)
+    try:
+        api.tuning_set("msm_rounds", rounds)
+        got, _ = api.msm(bases, sc, n)
+    finally:
+        api.tuning_set("msm_rounds", -1)
+    assert got == cref.msm(bases, sc, n, False, cref.max_threads())

@@ -220,12 +220,12 @@ def forced_rounds():
         for name in ("pair_k1", "pair_k2", "pair_k3"):
             api.tuning_set(name, k)
     yield force
-    for name, v in (("msm_rounds", -1), ("prover_rounds_w", -1), ("prover_rounds_h", -1), ("pair_k1", 32), ("pair_k2", 32),
-                    ("pair_k3", 32)):
+    for name, v in (("msm_rounds", -1), ("prover_rounds_w", -1), ("prover_rounds_h", -1), ("pair_k1", 16), ("pair_k2", 16),
+                    ("pair_k3", 16)):
         api.tuning_set(name, v)
 
 
-@pytest.mark.parametrize("rounds,k", [(1, 16), (2, 16), (3, 16), (3, 32), (2, 64)])
+@pytest.mark.parametrize("rounds,k", [(1, 16), (2, 16), (3, 16), (3, 32), (2, 8)])
 @pytest.mark.parametrize("g2", [False, True])
 def test_msm_pair_rounds_forced_edge_cases(lib, fixed_bases, forced_rounds, g2, rounds, k):
     """The edge-case MSMs again with the pair rounds forced on: equal points (tangent pairs), opposite points (infinity

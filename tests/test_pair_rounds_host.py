@@ -46,7 +46,7 @@ def _check(g2, pts, scalars, c, rounds, k):
 
 
 @pytest.mark.parametrize("g2", [False, True])
-@pytest.mark.parametrize("rounds,k", [(0, 4), (1, 4), (2, 4), (3, 4), (3, 16), (2, 32), (1, 64)])
+@pytest.mark.parametrize("rounds,k", [(0, 4), (1, 4), (2, 4), (3, 4), (3, 16), (2, 32), (1, 8)])
 def test_pair_rounds_uniform(lib, fixed_bases, g2, rounds, k):
     rng = random.Random(rounds * 10 + k + g2)
     n = 24 if g2 else 60
