@@ -17,8 +17,11 @@
  *                       readHeader and the three error checks (yarn.lock:987-999)
  *   nzcp_prove_batch    no snarkjs equivalent (one proof per call there); BASELINE.json configs[2] batch mode
  *   nzcp_ntt[_coset]    ffjavascript engine_fft.js Fr.fft / Fr.ifft, engine_applykey.js batchApplyKey (yarn.lock:408-416)
- *   nzcp_msm            ffjavascript engine_multiexp.js G1/G2.multiExpAffine (yarn.lock:408-416) over wasmcurves
- *                       build_multiexp.js (yarn.lock:1132-1135)
+ *   nzcp_msm, nzcp_msm_var, nzcp_msm_plan_*
+ *                       ffjavascript engine_multiexp.js G1/G2.multiExpAffine (yarn.lock:408-416) over wasmcurves
+ *                       build_multiexp.js (yarn.lock:1132-1135); the *_partial / sum_partials pair is the per-rank half of
+ *                       the split MSM of BASELINE.json configs[4]
+ *   nzcp_zkey_selfcheck no snarkjs equivalent: the format facts of SURVEY.md 8c-3, for the first real key
  *   nzcp_field_op       wasmcurves build_f1m.js f1m_mul / f1m_add / f1m_sub (yarn.lock:1132-1135)
  *   nzcp_synth_*        snarkjs zkey_new.js with a known tau in place of the ptau file /root/reference/Makefile:31 names;
  *                       shapes from circuits/nzcp_exampleTest.circom:4 and circuits/nzcp_liveTest.circom:4
@@ -98,6 +101,26 @@ int nzcp_zkey_load(const uint8_t* bytes, size_t len, int device, nzcp_zkey** out
 int nzcp_zkey_info_get(const nzcp_zkey* zk, nzcp_zkey_info* info);
 void nzcp_zkey_free(nzcp_zkey* zk);
 
+/* Format self-checks on a .zkey image -- what a snarkjs-made Groth16 key must satisfy, checked without a
+ * reference implementation: moduli, section sizes, canonical coefficient values, the nPublic+1 appended public-input rows
+ * (value R^2 mod r: pins the "coef * R^2" convention of section 4), and every base point of sections 3, 5-9 and of the header
+ * on its curve.  The point checks run on `device`.  Returns NZCP_OK when the file could be examined; the verdict is
+ * report->ok. */
+typedef struct nzcp_zkey_check {
+  uint32_t n_vars, n_public, domain_size;
+  uint32_t n_constraints;      /* constraint index of the first appended public-input row */
+  uint64_t n_coefs;
+  uint64_t bad_coef_values;    /* section 4 values >= r */
+  uint64_t bad_coef_indices;   /* records with matrix > 1, constraint >= domainSize or signal >= nVars */
+  uint64_t off_curve[6];       /* per section A(5), B1(6), B2(7), C(8), H(9), IC(3): points off the curve / non-canonical */
+  uint64_t infinity[6];        /* per section: (0,0) infinity markers (informational) */
+  uint32_t header_moduli_ok;   /* q, r are the BN254 moduli */
+  uint32_t header_points_ok;   /* alpha1, beta1, delta1 on G1, beta2, gamma2, delta2 on the twist, none at infinity */
+  uint32_t public_rows_ok;     /* last nPublic+1 coefficient records = (A, nConstraints+i, i, R^2 mod r) */
+  uint32_t ok;                 /* every check passed */
+} nzcp_zkey_check;
+int nzcp_zkey_selfcheck(const uint8_t* bytes, size_t len, int device, nzcp_zkey_check* report);
+
 /* Work buffers + streams for proofs against `zk`.  Several provers may share one zkey (one per host thread). */
 int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out);
 void nzcp_prover_free(nzcp_prover* p);
@@ -120,7 +143,7 @@ int nzcp_prove_device(nzcp_prover* p, const void* d_witness, const uint8_t* r, c
                       nzcp_prove_debug* dbg);
 /* Device pointer of the prover's own witness buffer (n_vars * 32 B), for callers that fill it themselves. */
 void* nzcp_prover_witness_buffer(nzcp_prover* p);
-/* Number of kernel launches issued by this prover so far. */
+/* Number of kernel launches issued for this prover so far (NULL: by the whole process). */
 uint64_t nzcp_prover_launch_count(const nzcp_prover* p);
 
 /* ---- standalone kernels (BASELINE config 4: NTT + MSM sweeps; also the fine-grained parity tests) ---- */
@@ -132,6 +155,24 @@ int nzcp_ntt_coset(uint8_t* data, int log_n, int batch, int device, float* kerne
  * scalars.  window_bits = 0 picks the default.  out = plain affine point (64 / 128 bytes). */
 int nzcp_msm(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int g2, int window_bits, int device,
              uint8_t* out, float* kernel_ms);
+/* MSM plans: a base set made resident once, any number of scalar vectors against it (csrc/msm_plan.cu).
+ *   mode 0  fixed-base: the bases are expanded into the 2^(c w) window table once (what nzcp_zkey_load does per section)
+ *   mode 1  variable-base: no table -- ffjavascript multiExpAffine's contract (arbitrary bases per call) at one pass over them
+ * build_ms (optional) = host wall time of the upload + table build.  Scalars are host buffers of n_scalars <= n_points
+ * plain 32-byte values. */
+typedef struct nzcp_msm_plan nzcp_msm_plan;
+int nzcp_msm_plan_create(const uint8_t* bases, size_t n_points, int g2, int window_bits, int mode, int device,
+                         nzcp_msm_plan** out, float* build_ms);
+void nzcp_msm_plan_free(nzcp_msm_plan* p);
+int nzcp_msm_plan_run(nzcp_msm_plan* p, const uint8_t* scalars, size_t n_scalars, uint8_t* out, float* kernel_ms);
+/* Split MSM (BASELINE.json configs[4]): the result stays in HBM as ONE extended-Jacobian point (x, y, zz,
+ * zzz Montgomery: 128 B for G1, 256 B for G2) written to the device pointer d_out, e.g. this rank's slot of an NCCL
+ * all-gather buffer.  nzcp_msm_sum_partials then adds `count` such points on the GPU and returns the plain affine sum. */
+int nzcp_msm_plan_run_partial(nzcp_msm_plan* p, const uint8_t* scalars, size_t n_scalars, void* d_out, float* kernel_ms);
+int nzcp_msm_sum_partials(const void* d_partials, size_t count, int g2, int device, uint8_t* out);
+/* One-shot variable-base MSM.  ms (optional): [0] host wall time of the whole call incl. uploads, [1] kernel time. */
+int nzcp_msm_var(const uint8_t* bases, const uint8_t* scalars, size_t n_points, int g2, int window_bits, int device,
+                 uint8_t* out, float ms[2]);
 /* Device self-test of the field / curve arithmetic against the host build of the same code; returns the number of
  * mismatches in *n_bad (0 = pass). */
 int nzcp_selftest(int device, uint64_t seed, uint32_t n_cases, uint32_t* n_bad);
@@ -142,7 +183,10 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
 /* Tuning knobs for experiments and tests (process-wide, read when a plan is created / a run is launched):
  *   "msm_rounds"  batched-affine pair rounds per MSM: -1 = automatic (by size), 0..3 forced
  *   "prover_rounds_w" / "prover_rounds_h"  the same for a prover's witness MSMs / H MSM (read by nzcp_prover_create)
- *   "pair_k1" / "pair_k2" / "pair_k3"  additions per thread in round 1 / 2 / 3: 4, 8, 16 or 32 */
+ *   "pair_k1" / "pair_k2" / "pair_k3"  additions per thread in round 1 / 2 / 3: 4, 8, 16 or 32
+ *   "stage_mode"  host witness upload in nzcp_prove*: -1 = automatic (pageable memory through the prover's pinned staging
+ *                 buffer in chunks, caller-pinned memory directly), 0 = always direct, 1 = always staged
+ *   "stage_chunk_kb"  staging chunk size in KiB (default 1024) */
 int nzcp_tuning_set(const char* name, int value);
 
 /* Integer-pipe microbenchmark (the MSM / NTT roofline denominator): out[0] = IMAD.WIDE.U32 (32x32->64 multiply-add) per

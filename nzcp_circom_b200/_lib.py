@@ -30,6 +30,14 @@ class ZkeyInfo(C.Structure):
                 ("device_bytes", C.c_uint64)]
 
 
+class ZkeyCheck(C.Structure):
+    _fields_ = [("n_vars", C.c_uint32), ("n_public", C.c_uint32), ("domain_size", C.c_uint32),
+                ("n_constraints", C.c_uint32), ("n_coefs", C.c_uint64), ("bad_coef_values", C.c_uint64),
+                ("bad_coef_indices", C.c_uint64), ("off_curve", C.c_uint64 * 6), ("infinity", C.c_uint64 * 6),
+                ("header_moduli_ok", C.c_uint32), ("header_points_ok", C.c_uint32), ("public_rows_ok", C.c_uint32),
+                ("ok", C.c_uint32)]
+
+
 class Proof(C.Structure):
     _fields_ = [("pi_a", C.c_uint8 * 64), ("pi_b", C.c_uint8 * 128), ("pi_c", C.c_uint8 * 64)]
 
@@ -62,6 +70,14 @@ SIGNATURES = {
     "nzcp_ntt": (C.c_int, [_U8P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "nzcp_ntt_coset": (C.c_int, [_U8P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "nzcp_msm": (C.c_int, [_U8P, _U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, _U8P, C.POINTER(C.c_float)]),
+    "nzcp_zkey_selfcheck": (C.c_int, [_U8P, C.c_size_t, C.c_int, C.POINTER(ZkeyCheck)]),
+    "nzcp_msm_plan_create": (C.c_int, [_U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P),
+                                       C.POINTER(C.c_float)]),
+    "nzcp_msm_plan_free": (None, [_P]),
+    "nzcp_msm_plan_run": (C.c_int, [_P, _U8P, C.c_size_t, _U8P, C.POINTER(C.c_float)]),
+    "nzcp_msm_plan_run_partial": (C.c_int, [_P, _U8P, C.c_size_t, _P, C.POINTER(C.c_float)]),
+    "nzcp_msm_sum_partials": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, _U8P]),
+    "nzcp_msm_var": (C.c_int, [_U8P, _U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, _U8P, C.POINTER(C.c_float)]),
     "nzcp_selftest": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
     "nzcp_field_op": (C.c_int, [C.c_int, C.c_int, _U8P, _U8P, _U8P, C.c_size_t, C.c_int]),
     "nzcp_intpipe_modes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),

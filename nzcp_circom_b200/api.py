@@ -6,7 +6,7 @@ top of it.  Everything computes on the GPU through libnzcp_prover.so; nothing he
 import ctypes as C
 
 from . import _lib
-from ._lib import NzcpError, Proof, ProveDebug, ZkeyInfo, addr, check
+from ._lib import NzcpError, Proof, ProveDebug, ZkeyCheck, ZkeyInfo, addr, check
 
 STAGE_NAMES = ("upload", "r1cs_eval", "ntt_join", "msm_a", "msm_b1", "msm_b2", "msm_c", "msm_h")
 
@@ -210,7 +210,8 @@ class ProverPool:
         return self._run("prove_device", [(d,) for d in d_witness_list], r, s, kw)
 
     def launch_count(self):
-        return self.provers[0].launch_count()
+        """Kernel launches issued for ALL provers of the pool so far."""
+        return sum(p.launch_count() for p in self.provers)
 
     def close(self):
         self._pool.shutdown(wait=True)
@@ -246,6 +247,85 @@ def msm(bases, scalars, n_points, g2=False, window_bits=0, device=0):
     check(_lib.load().nzcp_msm(addr(bases), addr(scalars), int(n_points), int(bool(g2)), int(window_bits), int(device),
                                addr(out), C.byref(ms)))
     return bytes(out), ms.value
+
+
+def msm_var(bases, scalars, n_points, g2=False, window_bits=0, device=0):
+    """One-shot variable-base MSM (no window table; ffjavascript multiExpAffine's contract).
+    -> (plain affine point bytes, {"wall_ms": whole call incl. uploads, "kernel_ms": sort + accumulate + reduce})."""
+    out = bytearray(128 if g2 else 64)
+    ms = (C.c_float * 2)()
+    check(_lib.load().nzcp_msm_var(addr(bases), addr(scalars), int(n_points), int(bool(g2)), int(window_bits), int(device),
+                                   addr(out), ms))
+    return bytes(out), {"wall_ms": float(ms[0]), "kernel_ms": float(ms[1])}
+
+
+XYZZ_BYTES = {False: 128, True: 256}   # one extended-Jacobian point (x, y, zz, zzz; Montgomery) in device memory
+
+
+class MsmPlan:
+    """A base set resident on one GPU (csrc/msm_plan.cu).  mode 0 = fixed-base (window table built once, as the prover
+    does per zkey section), mode 1 = variable-base (no table).  `run` returns the plain affine sum; `run_partial` leaves
+    the sum in HBM as one XYZZ point at `d_out` (a device pointer / CUDA tensor) for an NCCL all-gather."""
+
+    def __init__(self, bases, n_points, g2=False, window_bits=0, mode=1, device=0):
+        h = C.c_void_p()
+        ms = C.c_float()
+        check(_lib.load().nzcp_msm_plan_create(addr(bases) if n_points else None, int(n_points), int(bool(g2)),
+                                               int(window_bits), int(mode), int(device), C.byref(h), C.byref(ms)))
+        self._h = h
+        self.g2, self.n_points, self.mode, self.device, self.build_ms = bool(g2), int(n_points), int(mode), int(device), ms.value
+
+    def run(self, scalars, n_scalars=None):
+        n = self.n_points if n_scalars is None else int(n_scalars)
+        out = bytearray(128 if self.g2 else 64)
+        ms = C.c_float()
+        check(_lib.load().nzcp_msm_plan_run(self._h, addr(scalars) if n else None, n, addr(out), C.byref(ms)))
+        return bytes(out), ms.value
+
+    def run_partial(self, scalars, d_out, n_scalars=None):
+        n = self.n_points if n_scalars is None else int(n_scalars)
+        ms = C.c_float()
+        check(_lib.load().nzcp_msm_plan_run_partial(self._h, addr(scalars) if n else None, n, addr(d_out), C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().nzcp_msm_plan_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def msm_sum_partials(d_partials, count, g2=False, device=0):
+    """Sum of `count` XYZZ points in device memory (the gathered per-rank partials) -> plain affine bytes."""
+    out = bytearray(128 if g2 else 64)
+    check(_lib.load().nzcp_msm_sum_partials(addr(d_partials), int(count), int(bool(g2)), int(device), addr(out)))
+    return bytes(out)
+
+
+def zkey_selfcheck(zkey, device=0):
+    """Format self-checks of SURVEY.md 8c-3 on a .zkey image (path | bytes-like | {"type": "mem"}) -> dict; ["ok"] is
+    the verdict.  Meant for the first REAL snarkjs-made key: it pins the section-4 `coef * R^2` convention, the moduli
+    and that every base point is on its curve, without needing snarkjs."""
+    data = _as_bytes_like(zkey)
+    rep = ZkeyCheck()
+    check(_lib.load().nzcp_zkey_selfcheck(addr(data), _nbytes(data), int(device), C.byref(rep)))
+    names = ("A", "B1", "B2", "C", "H", "IC")
+    return {"ok": bool(rep.ok), "n_vars": rep.n_vars, "n_public": rep.n_public, "domain_size": rep.domain_size,
+            "n_constraints": rep.n_constraints, "n_coefs": rep.n_coefs, "bad_coef_values": rep.bad_coef_values,
+            "bad_coef_indices": rep.bad_coef_indices, "off_curve": dict(zip(names, [int(x) for x in rep.off_curve])),
+            "infinity": dict(zip(names, [int(x) for x in rep.infinity])), "header_moduli_ok": bool(rep.header_moduli_ok),
+            "header_points_ok": bool(rep.header_points_ok), "public_rows_ok": bool(rep.public_rows_ok)}
 
 
 def selftest(device=0, seed=1, n_cases=4096):

@@ -27,11 +27,15 @@ struct CudaError : std::runtime_error {
     }                                                                                                \
   } while (0)
 
-extern std::atomic<uint64_t> g_launch_count;  // every kernel launch of this library (bench.py "gpu_launches")
-#define NZCP_LAUNCH_CHECK()                \
-  do {                                     \
-    nzcp::g_launch_count.fetch_add(1);     \
-    NZCP_CUDA(cudaGetLastError());         \
+extern std::atomic<uint64_t> g_launch_count;  // every kernel launch of this library, process-wide
+// Launches are also charged to the prover the calling thread is working for (prove_impl points this at the prover's own
+// counter for the duration of the call): nzcp_prover_launch_count / bench.py "gpu_launches" are per prover.
+extern thread_local std::atomic<uint64_t>* t_launch_sink;
+#define NZCP_LAUNCH_CHECK()                                        \
+  do {                                                             \
+    nzcp::g_launch_count.fetch_add(1);                             \
+    if (nzcp::t_launch_sink) nzcp::t_launch_sink->fetch_add(1);    \
+    NZCP_CUDA(cudaGetLastError());                                 \
   } while (0)
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -77,12 +81,16 @@ struct MsmTable {
   size_t n_points = 0;   // including pad_front leading infinity points
   int c = 0, n_windows = 0;
   bool g2 = false;
+  bool owned = true;     // false: a view over the caller's bases (msm_table_view)
   size_t bytes = 0;
 };
 int msm_pick_window(size_t n_points);
 int msm_num_windows(int c);
+int msm_pick_window_free(size_t n_points);
 // d_bases: device array of n_src affine points; the table gets pad_front infinity points in front of them.
 void msm_table_create(MsmTable* t, const void* d_bases, size_t n_src, size_t pad_front, bool g2, int c, cudaStream_t st);
+// "Table" view of raw bases for the table-free path (one window, memory owned by the caller).
+void msm_table_view(MsmTable* t, void* d_bases, size_t n_points, bool g2, int c);
 void msm_table_destroy(MsmTable* t);
 
 static constexpr int kMsmMaxRounds = 3;
@@ -92,7 +100,10 @@ static constexpr int kMsmMaxRounds = 3;
 struct MsmSort {
   size_t n_points = 0;
   int c = 0, n_windows = 0;
-  size_t n_buckets = 0;     // 2^(c-1)
+  size_t n_buckets = 0;     // all buckets: group_buckets * n_groups
+  size_t group_buckets = 0; // 2^(c-1)
+  int n_groups = 1;         // 1: window-table mode (all windows share the buckets); n_windows: table-free mode
+  bool table_free = false;  // entries index the raw bases (no window table); window w accumulates into bucket group w
   bool smem_hist = false;   // histogram in shared memory (<= 2^15 buckets) or with global atomics
   uint32_t n_copies = 0;    // private copies of each bucket counter (smem path: one per block)
   uint32_t* counts = nullptr;
@@ -117,7 +128,7 @@ struct MsmSort {
   size_t round_max[kMsmMaxRounds + 1] = {0, 0, 0, 0};   // upper bound of the point count after round r
 };
 int msm_pick_rounds(size_t n_points, int c);
-void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds = -1);   // rounds < 0: msm_pick_rounds
+void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds = -1, bool table_free = false);   // rounds < 0: msm_pick_rounds
 void msm_sort_destroy(MsmSort* s);
 void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_t st);
 // After the stream drained: throws if the device flagged a scalar >= r.  Returns the number of non-zero digits.
@@ -130,6 +141,9 @@ struct MsmRun {
   void* buckets = nullptr;
   void* marg = nullptr;       // marginal bucket sums M_k[j], k < n_digits, j < 32
   int n_digits = 0;           // base-32 digits of a bucket id
+  int n_groups = 1, c = 0;    // bucket groups (table-free: one per window) and window bits, copied from the sort plan
+  uint32_t* marg_done = nullptr;   // per (group, digit): marginal blocks finished (self-resetting)
+  void* result = nullptr;     // device: the finished sum as one XYZZ point (msm_run_finish_device)
   uint32_t* heavy_list = nullptr;
   uint32_t* heavy_count = nullptr;   // [0] heavy buckets, [1] heavy chunks
   uint32_t* chunk_off = nullptr;
@@ -145,6 +159,8 @@ struct MsmRun {
 void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2);
 void msm_run_destroy(MsmRun* r);
 void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaStream_t st);
+void msm_run_finish_device(MsmRun* r, cudaStream_t st);
+void msm_sum_points(const void* d_pts, uint32_t count, bool g2, void* d_result, cudaStream_t st);
 G1XYZZ msm_run_finish_g1(const MsmRun* r);
 G2XYZZ msm_run_finish_g2(const MsmRun* r);
 float msm_run_accumulate_ms(const MsmRun* r);

@@ -68,7 +68,10 @@ struct DigitParams {
   uint32_t stride;    // points per window of the table the entries index (>= n_points)
   int c;
   int n_windows;
-  uint32_t n_buckets;
+  uint32_t n_buckets;     // buckets per group = 2^(c-1): the largest digit magnitude
+  uint32_t group_stride;  // 0: every window feeds the same bucket set (window-table mode); 2^(c-1): window w owns bucket
+                          // group w (table-free mode: entries index the raw bases, the windows are combined at the end)
+  uint32_t n_total;       // all buckets = n_buckets * (group_stride ? n_windows : 1)
 };
 
 __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, int pos, int c) {
@@ -151,7 +154,8 @@ msm_digits_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __res
     const uint32_t leader = __ffs(peers) - 1;
     const uint32_t rank = __popc(peers & ((1u << lane) - 1));
     uint32_t base = 0;
-    if (d && lane == leader) base = atomicAdd(&counts_or_cursors[(d - 1) * p.n_copies + copy], (uint32_t)__popc(peers));
+    if (d && lane == leader)
+      base = atomicAdd(&counts_or_cursors[(size_t)(d - 1 + (uint32_t)w * p.group_stride) * p.n_copies + copy], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     if (SCATTER && d) entries[base + rank] = ((uint32_t)w * p.stride + i) | (neg << 31);
   }
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(kSmemHistThreads, 1)
 msm_digits_smem_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* __restrict__ counts_or_offsets,
                        uint32_t* __restrict__ entries, uint32_t* __restrict__ flags) {
   extern __shared__ uint32_t hist[];
-  for (uint32_t b = threadIdx.x; b < p.n_buckets; b += blockDim.x)
+  for (uint32_t b = threadIdx.x; b < p.n_total; b += blockDim.x)
     hist[b] = SCATTER ? counts_or_offsets[b * p.n_copies + blockIdx.x] : 0u;
   __syncthreads();
   const uint32_t per_block = ((p.n_points + gridDim.x - 1) / gridDim.x + 31) & ~31u;   // whole warps stay together
@@ -209,7 +213,7 @@ msm_digits_smem_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* 
         carry = 0;
       }
       if (d) {   // shared-memory atomics: same-address lanes (the witness's digit 1) serialise on the SM, cheaply
-        const uint32_t pos = atomicAdd(&hist[d - 1], 1u);
+        const uint32_t pos = atomicAdd(&hist[d - 1 + (uint32_t)w * p.group_stride], 1u);
         if (SCATTER) entries[pos] = ((uint32_t)w * p.stride + i) | (neg << 31);
       }
     }
@@ -218,7 +222,7 @@ msm_digits_smem_kernel(const Fr* __restrict__ scalars, DigitParams p, uint32_t* 
   if (!SCATTER) {
     if (bad) atomicOr(&flags[1], bad);
     __syncthreads();
-    for (uint32_t b = threadIdx.x; b < p.n_buckets; b += blockDim.x) counts_or_offsets[b * p.n_copies + blockIdx.x] = hist[b];
+    for (uint32_t b = threadIdx.x; b < p.n_total; b += blockDim.x) counts_or_offsets[b * p.n_copies + blockIdx.x] = hist[b];
   }
 }
 
@@ -512,6 +516,18 @@ msm_pair_backward_kernel(const Affine<F>* __restrict__ src, const uint32_t* __re
   msm_pair_backward_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, dst, scratch, inv_prod);
 }
 
+// L2-coherent load of an object another block of the same grid wrote (after its __threadfence + counter increment).
+template <class T>
+__device__ __forceinline__ T load_cg(const T* p) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  T r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldcg(s + i);
+  return r;
+}
+
 template <class T>
 __device__ __forceinline__ T shfl_down_obj(const T& v, unsigned delta) {
   T r;
@@ -652,12 +668,37 @@ msm_combine_heavy2_kernel(const uint32_t* __restrict__ heavy_list, const uint32_
 // (suffix scan + tree sum through shuffles); the host finishes with  T + sum_k 32^k S_k  (T = sum of all buckets).
 static constexpr int kMargThreads = 128;
 
+// Suffix scan + tree sum of one digit's 32 marginals by one warp: returns sum_j j * M[j] (lane 0), *total = sum_j M[j].
+template <class F>
+__device__ __forceinline__ XYZZ<F> warp_weighted_sum(XYZZ<F> run, uint32_t lane, XYZZ<F>* total) {
+  for (uint32_t d = 1; d < 32; d <<= 1) {
+    XYZZ<F> o = shfl_down_obj(run, d);
+    if (lane + d < 32) xyzz_add(run, o);
+  }
+  *total = run;                                                  // lane 0: sum of all 32
+  XYZZ<F> leaf = lane >= 1 ? run : XYZZ<F>::inf();              // sum_{j>=1} suffix_j = sum_j j M[j]
+  for (uint32_t off = 16; off >= 1; off >>= 1) {
+    XYZZ<F> o = shfl_down_obj(leaf, off);
+    xyzz_add(leaf, o);
+  }
+  return leaf;
+}
+
+// Grid = n_groups * n_digits * 32 blocks: block (g, k, j) sums the buckets of group g whose k-th base-32 digit is j.  The
+// LAST of a digit's 32 blocks to finish (a counter per (g, k), reset by that block for the next launch) also folds the 32
+// marginals into S_k = sum_j j M_k[j] with its first warp -- the former second launch (three lone warps, ~115 us on the
+// critical path of every MSM) now starts the moment its inputs exist.
+// out[g * (n_digits + 1) + k] = S_k of group g, out[g * (n_digits + 1) + n_digits] = T = sum of the group's buckets.
 template <class F>
 __global__ void __launch_bounds__(kMargThreads)
-msm_marginal_kernel(const XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ marg, uint32_t bits) {
+msm_marginal_kernel(const XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ marg, XYZZ<F>* __restrict__ out,
+                    uint32_t* __restrict__ done, uint32_t bits, uint32_t n_digits) {
   extern __shared__ unsigned char heavy_sm_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_sm_raw);
-  const uint32_t k = blockIdx.x >> 5, j = blockIdx.x & 31;      // digit position, digit value
+  __shared__ uint32_t is_last;
+  const uint32_t gk = blockIdx.x >> 5, j = blockIdx.x & 31;     // (group, digit position), digit value
+  const uint32_t g = gk / n_digits, k = gk - g * n_digits;
+  const XYZZ<F>* bk = buckets + ((size_t)g << bits);
   const uint32_t lo_bits = 5 * k;
   const uint32_t dig_bits = bits - lo_bits < 5 ? bits - lo_bits : 5;
   XYZZ<F> acc = XYZZ<F>::inf();
@@ -666,32 +707,68 @@ msm_marginal_kernel(const XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ m
     const uint32_t lo_mask = (1u << lo_bits) - 1;
     for (uint32_t idx = threadIdx.x; idx < count; idx += blockDim.x) {
       const uint32_t v = (idx & lo_mask) | (j << lo_bits) | ((idx >> lo_bits) << (lo_bits + dig_bits));
-      xyzz_add(acc, buckets[v]);
+      xyzz_add(acc, bk[v]);
     }
   }
   acc = block_sum(acc, sm);
-  if (threadIdx.x == 0) marg[blockIdx.x] = acc;
+  if (threadIdx.x == 0) {
+    marg[blockIdx.x] = acc;
+    __threadfence();
+    const uint32_t prev = atomicAdd(&done[gk], 1u);
+    is_last = prev == 31u;
+    if (is_last) done[gk] = 0;                                   // ready for the next launch on this stream
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x >= 32) return;
+  __threadfence();
+  const uint32_t lane = threadIdx.x;
+  XYZZ<F> total;
+  XYZZ<F> leaf = warp_weighted_sum(load_cg(marg + gk * 32 + lane), lane, &total);   // marginals beyond the digit's range are infinity
+  if (lane == 0) {
+    out[g * (n_digits + 1) + k] = leaf;
+    if (k == 0) out[g * (n_digits + 1) + n_digits] = total;
+  }
 }
 
-// One warp per digit position: out[k] = sum_j j * M_k[j]; warp 0 also writes the total T = sum_j M_0[j] to out[n_digits].
+// sum_g 2^(c g) * (T_g + sum_k 32^k S_{g,k}) on the device (one warp; lane g folds group g, then a shuffle tree applies
+// the 2^(c g) factors by repeated doubling).  The prover finishes on the host instead (a dozen group operations are
+// faster there); this kernel exists for results that must stay in HBM: the per-rank partial sums of a split MSM.
 template <class F>
 __global__ void __launch_bounds__(32)
-msm_weighted_kernel(const XYZZ<F>* __restrict__ marg, XYZZ<F>* __restrict__ out, uint32_t n_digits) {
-  const uint32_t k = blockIdx.x, lane = threadIdx.x;
-  XYZZ<F> run = marg[k * 32 + lane];                             // marginals beyond the digit's range are infinity
-  for (uint32_t d = 1; d < 32; d <<= 1) {
-    XYZZ<F> o = shfl_down_obj(run, d);
-    if (lane + d < 32) xyzz_add(run, o);
+msm_finish_kernel(const XYZZ<F>* __restrict__ out, XYZZ<F>* __restrict__ result, uint32_t n_groups, uint32_t n_digits, int c) {
+  const uint32_t lane = threadIdx.x;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (lane < n_groups) {
+    const XYZZ<F>* w = out + lane * (n_digits + 1);
+    for (int k = (int)n_digits - 1; k >= 0; k--) {
+      if (!acc.is_inf())
+        for (int d = 0; d < 5; d++) acc = xyzz_dbl(acc);
+      xyzz_add(acc, w[k]);
+    }
+    xyzz_add(acc, w[n_digits]);
   }
-  XYZZ<F> leaf = lane >= 1 ? run : XYZZ<F>::inf();              // sum_{j>=1} suffix_j = sum_j j M[j]
-  for (uint32_t off = 16; off >= 1; off >>= 1) {
-    XYZZ<F> o = shfl_down_obj(leaf, off);
-    xyzz_add(leaf, o);
+  // tree: acc[l] += 2^(c * off) * acc[l + off]
+  for (uint32_t off = 1; off < 32; off <<= 1) {
+    XYZZ<F> o = shfl_down_obj(acc, off);
+    if ((lane & (2 * off - 1)) == 0 && lane + off < n_groups) {
+      for (uint32_t d = 0; d < (uint32_t)c * off; d++)
+        if (!o.is_inf()) o = xyzz_dbl(o);
+      xyzz_add(acc, o);
+    }
   }
-  if (lane == 0) {
-    out[k] = leaf;
-    if (k == 0) out[n_digits] = run;
-  }
+  if (lane == 0) *result = acc;
+}
+
+// result = sum of `count` points (the gathered per-rank partials of a split MSM): one block, tree in shared memory.
+template <class F>
+__global__ void __launch_bounds__(kHeavyThreads)
+msm_sum_points_kernel(const XYZZ<F>* __restrict__ pts, uint32_t count, XYZZ<F>* __restrict__ result) {
+  extern __shared__ unsigned char heavy_sm_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_sm_raw);
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t j = threadIdx.x; j < count; j += blockDim.x) xyzz_add(acc, pts[j]);
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) *result = acc;
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -705,6 +782,24 @@ int msm_pick_window(size_t n) {
   if (lg <= 16) return 12;
   if (lg <= 18) return 14;
   return 16;
+}
+
+// Table-free path: every window has its own 2^(c-1) buckets, reduced separately, so the optimum is a little below the
+// shared-bucket one.  Cost model in Fq products: W * (10 n + 2^(c-1) * 14 * (digits + 1)), W * 2^(c-1) <= 2^19.
+int msm_pick_window_free(size_t n) {
+  int best = 2;
+  double best_cost = 1e300;
+  for (int c = 2; c <= 16; c++) {
+    const int w = msm_num_windows(c);
+    const double nb = (double)((size_t)1 << (c - 1));
+    if (w * nb > (double)(1 << 19)) break;
+    const double cost = w * (10.0 * (double)n + nb * 14.0 * ((c - 1 + 4) / 5 + 1));
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
 }
 
 int msm_num_windows(int c) {
@@ -763,19 +858,33 @@ void msm_table_create(MsmTable* t, const void* d_bases, size_t n_src, size_t pad
   NZCP_LAUNCH_CHECK();
 }
 
+void msm_table_view(MsmTable* t, void* d_bases, size_t n_points, bool g2, int c) {
+  *t = MsmTable();
+  t->pts = d_bases;
+  t->n_points = n_points;
+  t->c = c;
+  t->n_windows = 1;
+  t->g2 = g2;
+  t->owned = false;
+}
+
 void msm_table_destroy(MsmTable* t) {
-  cudaFree(t->pts);
+  if (t->owned) cudaFree(t->pts);
   *t = MsmTable();
 }
 
-void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds) {
+void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds, bool table_free) {
   *s = MsmSort();
   if (c < 2 || c > 20) throw std::runtime_error("msm: window size out of range");
   s->n_points = n_points;
   s->c = c;
   s->rounds = rounds < 0 ? msm_pick_rounds(n_points, c) : (rounds > kMsmMaxRounds ? kMsmMaxRounds : rounds);
   s->n_windows = msm_num_windows(c);
-  s->n_buckets = (size_t)1 << (c - 1);
+  s->table_free = table_free;
+  s->n_groups = table_free ? s->n_windows : 1;
+  s->group_buckets = (size_t)1 << (c - 1);
+  s->n_buckets = s->group_buckets * s->n_groups;
+  if (s->n_buckets > ((size_t)1 << 19)) throw std::runtime_error("msm: too many buckets (window size too large for the table-free path)");
   size_t max_entries = (size_t)s->n_windows * n_points;
   if (max_entries >= ((size_t)1 << 31)) throw std::runtime_error("msm: too many points");
   // task length L = clamp(pow2_floor(entries / kTargetTasks), 8, 64)  =>  tasks <= n_buckets + max(2 * target, entries / 64)
@@ -835,7 +944,8 @@ void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_
     }
     const uint32_t n_ctr = nb * n_copies;
     // entries index the table of the plan's full point count, so a shorter scalar vector still addresses T[w][i]
-    DigitParams dp{n_copies, (uint32_t)n_points, (uint32_t)s->n_points, s->c, s->n_windows, nb};
+    DigitParams dp{n_copies, (uint32_t)n_points, s->table_free ? 0u : (uint32_t)s->n_points, s->c, s->n_windows,
+                   (uint32_t)s->group_buckets, s->table_free ? (uint32_t)s->group_buckets : 0u, nb};
     const unsigned gp = div_up(n_points, 256);
     const size_t hist_bytes = (size_t)nb * sizeof(uint32_t);
     if (s->smem_hist) {
@@ -900,15 +1010,22 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
   }
   r->partial = dev_alloc<unsigned char>(sort->max_tasks * psz, &tot);
   r->buckets = dev_alloc<unsigned char>(sort->n_buckets * psz, &tot);
-  r->marg = dev_alloc<unsigned char>(kMaxDigits * 32 * psz, &tot);
+  r->n_groups = sort->n_groups;
+  r->c = sort->c;
+  r->marg = dev_alloc<unsigned char>((size_t)r->n_groups * kMaxDigits * 32 * psz, &tot);
+  r->marg_done = dev_alloc<uint32_t>((size_t)r->n_groups * kMaxDigits, &tot);
+  NZCP_CUDA(cudaMemset(r->marg_done, 0, (size_t)r->n_groups * kMaxDigits * sizeof(uint32_t)));
+  r->result = dev_alloc<unsigned char>(psz, &tot);
   r->heavy_list = dev_alloc<uint32_t>(sort->n_buckets, &tot);
   r->heavy_count = dev_alloc<uint32_t>(2, &tot);
   r->chunk_off = dev_alloc<uint32_t>(sort->n_buckets + 1, &tot);
   r->chunk_partial = dev_alloc<unsigned char>((sort->max_tasks / kHeavyChunk + sort->n_buckets + 1) * psz, &tot);
-  r->out = dev_alloc<unsigned char>((kMaxDigits + 1) * psz, &tot);
-  NZCP_CUDA(cudaMallocHost(&r->out_host, (kMaxDigits + 1) * psz));
-  memset(r->out_host, 0, (kMaxDigits + 1) * psz);
+  r->out = dev_alloc<unsigned char>((size_t)r->n_groups * (kMaxDigits + 1) * psz, &tot);
+  NZCP_CUDA(cudaMallocHost(&r->out_host, (size_t)r->n_groups * (kMaxDigits + 1) * psz));
+  memset(r->out_host, 0, (size_t)r->n_groups * (kMaxDigits + 1) * psz);
   r->n_digits = (sort->c - 1 + 4) / 5;
+  NZCP_CUDA(cudaFuncSetAttribute(msm_sum_points_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kHeavyThreads * sizeof(G2XYZZ))));
   if (sort->rounds > 0) {
     const size_t asz = g2 ? sizeof(G2Affine) : sizeof(G1Affine), fsz = asz / 2, pad = 128 * 64;
     r->round_pts[0] = dev_alloc<unsigned char>((sort->round_max[1] + pad) * asz, &tot);
@@ -925,6 +1042,8 @@ void msm_run_destroy(MsmRun* r) {
   cudaFree(r->partial);
   cudaFree(r->buckets);
   cudaFree(r->marg);
+  cudaFree(r->marg_done);
+  cudaFree(r->result);
   cudaFree(r->heavy_list);
   cudaFree(r->heavy_count);
   cudaFree(r->chunk_off);
@@ -942,7 +1061,8 @@ void msm_run_destroy(MsmRun* r) {
 
 template <class F>
 static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cudaStream_t st) {
-  if (t->c != s->c || t->n_points != s->n_points) throw std::runtime_error("msm: table and sort plan do not match");
+  if (t->c != s->c || t->n_points != s->n_points || t->n_windows != (s->table_free ? 1 : s->n_windows))
+    throw std::runtime_error("msm: table and sort plan do not match");
   const uint32_t nb = (uint32_t)s->n_buckets;
   const size_t psz = sizeof(XYZZ<F>);
   XYZZ<F>* partial = reinterpret_cast<XYZZ<F>*>(r->partial);
@@ -1009,11 +1129,35 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
   const uint32_t bits = (uint32_t)(s->c - 1);
   const uint32_t n_digits = (bits + 4) / 5;
   XYZZ<F>* marg = reinterpret_cast<XYZZ<F>*>(r->marg);
-  msm_marginal_kernel<F><<<n_digits * 32, kMargThreads, kMargThreads * psz, st>>>(buckets, marg, bits);
+  msm_marginal_kernel<F><<<(unsigned)s->n_groups * n_digits * 32, kMargThreads, kMargThreads * psz, st>>>(buckets, marg, out,
+                                                                                                      r->marg_done, bits, n_digits);
   NZCP_LAUNCH_CHECK();
-  msm_weighted_kernel<F><<<n_digits, 32, 0, st>>>(marg, out, n_digits);
+  NZCP_CUDA(cudaMemcpyAsync(r->out_host, r->out, (size_t)s->n_groups * (n_digits + 1) * psz, cudaMemcpyDeviceToHost, st));
+}
+
+// After msm_run_launch on the same stream: fold the run's digit sums into ONE point that stays on the device.
+void msm_run_finish_device(MsmRun* r, cudaStream_t st) {
+  if (r->g2)
+    msm_finish_kernel<Fq2><<<1, 32, 0, st>>>(reinterpret_cast<const G2XYZZ*>(r->out), reinterpret_cast<G2XYZZ*>(r->result),
+                                             (uint32_t)r->n_groups, (uint32_t)r->n_digits, r->c);
+  else
+    msm_finish_kernel<Fq><<<1, 32, 0, st>>>(reinterpret_cast<const G1XYZZ*>(r->out), reinterpret_cast<G1XYZZ*>(r->result),
+                                            (uint32_t)r->n_groups, (uint32_t)r->n_digits, r->c);
   NZCP_LAUNCH_CHECK();
-  NZCP_CUDA(cudaMemcpyAsync(r->out_host, r->out, (n_digits + 1) * psz, cudaMemcpyDeviceToHost, st));
+}
+
+// result (device, one XYZZ point) = sum of `count` XYZZ points in device memory.
+void msm_sum_points(const void* d_pts, uint32_t count, bool g2, void* d_result, cudaStream_t st) {
+  if (g2) {
+    NZCP_CUDA(cudaFuncSetAttribute(msm_sum_points_kernel<Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kHeavyThreads * sizeof(G2XYZZ))));
+    msm_sum_points_kernel<Fq2><<<1, kHeavyThreads, kHeavyThreads * sizeof(G2XYZZ), st>>>(
+        reinterpret_cast<const G2XYZZ*>(d_pts), count, reinterpret_cast<G2XYZZ*>(d_result));
+  } else {
+    msm_sum_points_kernel<Fq><<<1, kHeavyThreads, kHeavyThreads * sizeof(G1XYZZ), st>>>(
+        reinterpret_cast<const G1XYZZ*>(d_pts), count, reinterpret_cast<G1XYZZ*>(d_result));
+  }
+  NZCP_LAUNCH_CHECK();
 }
 
 void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaStream_t st) {
@@ -1027,15 +1171,22 @@ void msm_run_launch(MsmRun* r, const MsmSort* sort, const MsmTable* table, cudaS
 template <class F>
 static XYZZ<F> msm_run_finish_t(const MsmRun* r) {
   // sum_v v B_v = T + sum_k 32^k S_k : Horner over the digit positions (a handful of host group operations)
-  const XYZZ<F>* w = reinterpret_cast<const XYZZ<F>*>(r->out_host);
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (int k = r->n_digits - 1; k >= 0; k--) {
-    if (!acc.is_inf())
-      for (int d = 0; d < 5; d++) acc = xyzz_dbl(acc);
-    xyzz_add(acc, w[k]);
+  // table-free runs: one such sum per window, folded by Horner with c doublings per step (ffjavascript's own last step)
+  XYZZ<F> res = XYZZ<F>::inf();
+  for (int g = r->n_groups - 1; g >= 0; g--) {
+    const XYZZ<F>* w = reinterpret_cast<const XYZZ<F>*>(r->out_host) + (size_t)g * (r->n_digits + 1);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int k = r->n_digits - 1; k >= 0; k--) {
+      if (!acc.is_inf())
+        for (int d = 0; d < 5; d++) acc = xyzz_dbl(acc);
+      xyzz_add(acc, w[k]);
+    }
+    xyzz_add(acc, w[r->n_digits]);
+    if (!res.is_inf())
+      for (int d = 0; d < r->c; d++) res = xyzz_dbl(res);
+    xyzz_add(res, acc);
   }
-  xyzz_add(acc, w[r->n_digits]);
-  return acc;
+  return res;
 }
 
 G1XYZZ msm_run_finish_g1(const MsmRun* r) { return msm_run_finish_t<Fq>(r); }

@@ -18,6 +18,13 @@ namespace nzcp {
 
 extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;   // msm.cu
 std::atomic<uint64_t> g_launch_count{0};
+thread_local std::atomic<uint64_t>* t_launch_sink = nullptr;
+// "stage_mode" knob: how nzcp_prove moves a HOST witness to the GPU.  -1 = automatic: pageable memory (a Node Buffer, a
+// Python bytes object) goes through the prover's pinned staging buffer in chunks, so the CPU copy of chunk k+1 overlaps
+// the DMA of chunk k; memory the caller pinned (cudaHostAlloc / cudaHostRegister) is handed to the copy engine directly.
+// 0 = always direct (the driver stages pageable memory itself), 1 = always through the staging buffer.
+std::atomic<int> g_tune_stage_mode{-1};
+std::atomic<int> g_tune_stage_chunk_kb{1024};
 
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& s) { t_last_error = s; }
@@ -82,6 +89,9 @@ struct nzcp_zkey {
 
 struct nzcp_prover {
   nzcp_zkey* zk = nullptr;
+  int device = 0;                               // copy of zk->device: release must not touch a key freed before it
+  std::atomic<uint64_t> launches{0};            // kernel launches issued for this prover (nzcp_prover_launch_count)
+  uint8_t* h_stage = nullptr;                   // pinned staging buffer for pageable host witnesses (n_vars * 32 B, lazy)
   cudaStream_t st_main = nullptr;
   cudaStream_t st_msm[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev[20];
@@ -240,7 +250,8 @@ static nzcp_zkey* zkey_load_impl(const uint8_t* b, size_t len, int device) {
 
 static void prover_release(nzcp_prover* p) {
   if (!p) return;
-  cudaSetDevice(p->zk->device);
+  cudaSetDevice(p->device);
+  if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->st_main) cudaStreamDestroy(p->st_main);
   for (int i = 0; i < 4; i++)
     if (p->st_msm[i]) cudaStreamDestroy(p->st_msm[i]);
@@ -262,6 +273,7 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
   use_device(zk->device);
   std::unique_ptr<nzcp_prover, void (*)(nzcp_prover*)> p(new nzcp_prover(), prover_release);
   p->zk = zk;
+  p->device = zk->device;
   NZCP_CUDA(cudaStreamCreateWithFlags(&p->st_main, cudaStreamNonBlocking));
   for (int i = 0; i < 4; i++) NZCP_CUDA(cudaStreamCreateWithFlags(&p->st_msm[i], cudaStreamNonBlocking));
   for (int i = 0; i < 20; i++) {
@@ -300,6 +312,37 @@ static void random_fr(uint8_t out[32]) {
   fclose(f);
 }
 
+// Host witness -> p->d_wtns on stream `st`.  Pageable source memory is copied through the prover's pinned staging buffer
+// in chunks (CPU copy of chunk k+1 overlaps the DMA of chunk k, and the stream is never blocked behind the driver's own
+// pageable-memory path, which serialises with every other stream of the process); pinned sources go straight to the
+// copy engine.  The staging buffer is as large as the witness, so no slot is reused inside one proof, and the previous
+// proof of this prover has drained its streams before the call returned.
+static void upload_witness(nzcp_prover* p, const uint8_t* h_witness, size_t bytes, cudaStream_t st) {
+  int mode = g_tune_stage_mode.load();
+  bool stage = mode == 1;
+  if (mode < 0) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, h_witness) != cudaSuccess) {
+      cudaGetLastError();
+      stage = true;
+    } else {
+      stage = attr.type == cudaMemoryTypeUnregistered;
+    }
+  }
+  if (!stage) {
+    NZCP_CUDA(cudaMemcpyAsync(p->d_wtns, h_witness, bytes, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  if (!p->h_stage) NZCP_CUDA(cudaHostAlloc((void**)&p->h_stage, (size_t)p->zk->n_vars * sizeof(Fr), cudaHostAllocDefault));
+  size_t chunk = (size_t)g_tune_stage_chunk_kb.load() * 1024;
+  if (chunk < 65536) chunk = 65536;
+  for (size_t off = 0; off < bytes; off += chunk) {
+    const size_t len = bytes - off < chunk ? bytes - off : chunk;
+    memcpy(p->h_stage + off, h_witness + off, len);
+    NZCP_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(p->d_wtns) + off, p->h_stage + off, len, cudaMemcpyHostToDevice, st));
+  }
+}
+
 // Event slots: 0 start, 1 upload done, 2 eval done, 3 ntt+join done, 4 msm H done, 5 witness sort done,
 // 6..13 msm A,B1,B2,C (begin,end), 14 h sort done
 static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_witness_ext, const uint8_t* r_in,
@@ -313,10 +356,20 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
   use_device(zk->device);
   const size_t n = zk->domain_size, m = zk->n_vars;
   cudaStream_t sm = p->st_main;
+  struct Sink {   // kernel launches of this call are charged to this prover
+    std::atomic<uint64_t>* prev;
+    explicit Sink(std::atomic<uint64_t>* c) : prev(t_launch_sink) { t_launch_sink = c; }
+    ~Sink() { t_launch_sink = prev; }
+  } sink(&p->launches);
+  auto drain = [&] {   // leave no work in flight behind an error: the prover (and its buffers) may be reused or freed
+    for (int k = 0; k < 4; k++) cudaStreamSynchronize(p->st_msm[k]);
+    cudaStreamSynchronize(sm);
+  };
+  try {
   NZCP_CUDA(cudaEventRecord(p->ev[0], sm));
   const Fr* d_w = d_witness_ext;
   if (h_witness) {
-    NZCP_CUDA(cudaMemcpyAsync(p->d_wtns, h_witness, m * sizeof(Fr), cudaMemcpyHostToDevice, sm));
+    upload_witness(p, h_witness, m * sizeof(Fr), sm);
     d_w = p->d_wtns;
   }
   NZCP_CUDA(cudaEventRecord(p->ev[1], sm));
@@ -351,6 +404,10 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
   msm_run_launch(&p->run_h, &p->sort_h, &zk->tab_h, sm);
   NZCP_CUDA(cudaEventRecord(p->ev[4], sm));
   if (dbg && dbg->h_scalars) NZCP_CUDA(cudaMemcpyAsync(dbg->h_scalars, p->d_h, n * sizeof(Fr), cudaMemcpyDeviceToHost, sm));
+  } catch (...) {
+    drain();
+    throw;
+  }
   // While the GPU works: the blinding terms that depend only on r, s and the key (r*delta1, s*delta1, s*delta2,
   // -rs*delta1) -- four of the six scalar multiplications of the final combination leave the latency path.
   const Fr r = fp_from_bytes_plain<FrParams>(rb), s = fp_from_bytes_plain<FrParams>(sb);
@@ -389,9 +446,7 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
     NZCP_CUDA(cudaStreamSynchronize(sm));             // H: only its Horner tail, four additions and one inversion remain
     ent_h = msm_sort_check(&p->sort_h);
   } catch (const std::runtime_error& e) {
-    // leave no work in flight behind an error: the prover (and its buffers) may be reused or freed right away
-    for (int k = 0; k < 4; k++) cudaStreamSynchronize(p->st_msm[k]);
-    cudaStreamSynchronize(sm);
+    drain();
     if (dynamic_cast<const CudaError*>(&e) || dynamic_cast<const ApiError*>(&e)) throw;
     throw ApiError(NZCP_E_RANGE, e.what());
   }
@@ -527,7 +582,7 @@ int nzcp_prove_device(nzcp_prover* p, const void* d_witness, const uint8_t* r, c
 
 void* nzcp_prover_witness_buffer(nzcp_prover* p) { return p ? p->d_wtns : nullptr; }
 
-uint64_t nzcp_prover_launch_count(const nzcp_prover*) { return g_launch_count.load(); }
+uint64_t nzcp_prover_launch_count(const nzcp_prover* p) { return p ? p->launches.load() : g_launch_count.load(); }
 
 int nzcp_prove_batch(nzcp_zkey* zk, const uint8_t* const* wtns, const size_t* wtns_len, size_t n_proofs, const uint8_t* r,
                      const uint8_t* s, nzcp_proof* proofs, int n_provers, int* status) {

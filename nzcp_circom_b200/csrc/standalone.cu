@@ -11,6 +11,7 @@ namespace nzcp {
 extern std::atomic<int> g_tune_rounds;                   // msm.cu
 extern std::atomic<int> g_tune_pair_k[kMsmMaxRounds];
 extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;
+extern std::atomic<int> g_tune_stage_mode, g_tune_stage_chunk_kb;   // prover.cu
 
 G1Affine g1_generator();  // synth.cu
 Fr host_fr_root(int k);     // ntt.cu
@@ -710,6 +711,8 @@ int nzcp_tuning_set(const char* name, int value) {
     else if (k == "pair_k1") g_tune_pair_k[0].store(value);
     else if (k == "pair_k2") g_tune_pair_k[1].store(value);
     else if (k == "pair_k3") g_tune_pair_k[2].store(value);
+    else if (k == "stage_mode") g_tune_stage_mode.store(value);
+    else if (k == "stage_chunk_kb") g_tune_stage_chunk_kb.store(value);
     else throw ApiError(NZCP_E_ARG, "unknown tuning knob: " + k);
   });
 }

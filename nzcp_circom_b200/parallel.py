@@ -2,17 +2,18 @@
 
 * Batch mode -- independent proofs sharded `i mod world`; the proving key is replicated on every GPU; NO collective on
   the data path.  The only exchange is gathering the 256-byte proofs to the caller (all_gather_object).
-* Split MSM -- one large MSM partitioned by point range; each rank reduces its slice to ONE point with the full
-  single-GPU pipeline (nzcp_msm), then a single all-gather of 64 / 128 bytes per rank (NCCL over NVLink when the
-  backend is nccl) and world-1 group additions on every rank.  Latency-bound (~10 us), bandwidth irrelevant.
+* Split MSM -- one large MSM partitioned by point range; each rank reduces its slice to ONE point that stays in HBM
+  (nzcp_msm_plan_run_partial), a single all-gather of 128 / 256 bytes per rank (NCCL over NVLink, device buffers on
+  both sides) and a kernel adds the world partials (nzcp_msm_sum_partials).  Latency-bound (~10 us), bandwidth irrelevant.
 
 The local compute functions are parameters so that the sharding / gather logic is testable on CPU with the gloo
 backend (tests/test_parallel.py); the defaults are the GPU paths of this package.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import api, verifier
+from . import api
 
 
 def shard_indices(n_items, rank, world):
@@ -73,48 +74,40 @@ def prove_batch(zkey, wtns_list, r_list=None, s_list=None, device=None, n_prover
     return out
 
 
-def _point_from_bytes(b, g2):
-    le = lambda o: int.from_bytes(b[o:o + 32], "little")  # noqa: E731
-    if g2:
-        v = [le(32 * i) for i in range(4)]
-        return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
-    x, y = le(0), le(32)
-    return None if x == 0 and y == 0 else (x, y)
-
-
-def _point_to_bytes(P, g2):
-    if P is None:
-        return bytes(128 if g2 else 64)
-    flat = [P[0][0], P[0][1], P[1][0], P[1][1]] if g2 else [P[0], P[1]]
-    return b"".join(int(v).to_bytes(32, "little") for v in flat)
-
-
-def msm_split(bases, scalars, n_points, g2=False, group=None, device=None, local_msm=None):
-    """sum_i s_i P_i with the point range split over the ranks of `group`.
+def msm_split(bases, scalars, n_points, g2=False, group=None, device=None, mode=1, local_partial=None, sum_partials=None):
+    """sum_i s_i P_i with the point range split over the ranks of `group` (BASELINE.json configs[4]).
 
     bases / scalars: the FULL arrays (bytes-like; every rank slices its own range).  Returns the plain affine result
-    (64 / 128 bytes) on every rank.  `local_msm(bases_slice, scalars_slice, n, g2) -> point bytes` defaults to the
-    single-GPU nzcp_msm."""
+    (64 / 128 bytes) on every rank.  Product path (defaults): each rank runs an MsmPlan on its slice (mode 1 =
+    variable-base, no window table; mode 0 = fixed-base), which leaves ONE extended-Jacobian point (128 / 256 B) in
+    HBM; one all-gather of those points over NCCL (NVLink / NVSwitch) straight from and into device memory; the world
+    partials are added by a kernel (nzcp_msm_sum_partials) and only the final affine point crosses to the host.
+
+    `local_partial(bases_slice, scalars_slice, n, g2) -> bytes` and `sum_partials(list_of_bytes, g2) -> bytes` replace the
+    two GPU steps so that the slicing / gather logic runs on CPU with gloo (tests/test_parallel.py)."""
     rank, world = _world(group)
     lo, hi = shard_range(n_points, rank, world)
     bsz = 128 if g2 else 64
-    bv, sv = memoryview(bases).cast("B"), memoryview(scalars).cast("B")
-    if local_msm is None:
+    bv, sv = np.frombuffer(bases, dtype=np.uint8), np.frombuffer(scalars, dtype=np.uint8)   # zero-copy views
+    b_slice, s_slice = bv[lo * bsz:hi * bsz], sv[lo * 32:hi * 32]
+    if (local_partial is None) != (sum_partials is None):
+        raise ValueError("local_partial and sum_partials must be injected together")
+    if local_partial is None:
         if device is None:
             device = rank % max(1, api.device_count())
-
-        def local_msm(b, s, n, g2_):
-            return api.msm(bytes(b), bytes(s), n, g2=g2_, device=device)[0]
-    part = local_msm(bv[lo * bsz:hi * bsz], sv[lo * 32:hi * 32], hi - lo, g2)
-    if world == 1:
-        return bytes(part)
-    backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine, group=group)       # the one exchange step: bsz bytes per rank
-    add = verifier.g2_add if g2 else verifier.g1_add
-    acc = None
-    for t in parts:
-        acc = add(acc, _point_from_bytes(bytes(t.cpu().numpy()), g2))
-    return _point_to_bytes(acc, g2)
+        dev = torch.device("cuda", device)
+        psz = api.XYZZ_BYTES[bool(g2)]
+        mine = torch.zeros(psz, dtype=torch.uint8, device=dev)
+        with api.MsmPlan(b_slice, hi - lo, g2=g2, mode=mode, device=device) as plan:
+            plan.run_partial(s_slice, mine)
+    else:
+        mine = torch.frombuffer(bytearray(local_partial(b_slice, s_slice, hi - lo, g2)), dtype=torch.uint8)
+    if world > 1:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)       # the one exchange step: one point per rank
+    else:
+        parts = [mine]
+    if sum_partials is None:
+        flat = torch.cat(parts)                          # device-to-device: world * psz contiguous bytes
+        return api.msm_sum_partials(flat, world, g2=g2, device=device)
+    return sum_partials([bytes(t.numpy()) for t in parts], g2)
