@@ -10,7 +10,10 @@ resident proving key).  Multi-GPU = batch sharding, no collective (weak scaling:
 
 `value`  : proofs/s with the witnesses already resident in HBM (nzcp_prove_device).
 `e2e`    : proofs/s through the reference-facing call (nzcp_prove_batch: .wtns images in pinned HOST memory in, the
-           proofs in host memory out; H2D + D2H inside the timed region).
+           proofs in host memory out; H2D + D2H inside the timed region, random r/s); `e2e.pageable` = the same from
+           ordinary pageable memory.
+`extras` : BASELINE configs[2] (1024 exampleTest-shape proofs sharded over the ranks) and configs[4] (one 2^24-point G1
+           MSM split over the ranks, NCCL gather of the partial sums) -- skipped with --no-extras.
 `roofline`: the dominant kernel of the step, timed live with CUDA events on its own stream inside the library.
 `cpu_baseline` / `--impl reference`: the C restatement of snarkjs groth16.prove (oracle/c) on the host cores -- NOT
            snarkjs itself (node is not installed on these boxes); labelled kind="port".
@@ -103,6 +106,43 @@ def make_workload(shape, device, n_witness, first_seed):
     return zkey, wtns, dims
 
 
+def workload_cache_dir():
+    d = os.environ.get("NZCP_BENCH_CACHE") or os.path.join(os.environ.get("TMPDIR", "/tmp"), "nzcp_bench_cache")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def make_workload_files(shape, n_witness, first_seed):
+    """The same workload as make_workload, written to files by a SEPARATE process: the reference arm must not map
+    libnzcp_prover.so (the synthetic key is made by the library's GPU setup kernel), so it only reads the result.
+    -> (zkey bytes, [wtns bytes], dims)."""
+    import subprocess
+    d = workload_cache_dir()
+    tag = "%s_s%d_n%d" % (shape, first_seed, n_witness)
+    meta = os.path.join(d, tag + ".json")
+    if not os.path.exists(meta):
+        code = ("import json,sys; sys.path.insert(0, %r); import bench\n"
+                "zkey, wtns, dims = bench.make_workload(%r, 0, %d, %d)\n"
+                "open(%r, 'wb').write(zkey)\n"
+                "[open(%r %% i, 'wb').write(w) for i, w in enumerate(wtns)]\n"
+                "json.dump(dims, open(%r + '.tmp', 'w'))\n"
+                % (ROOT, shape, n_witness, first_seed, os.path.join(d, tag + ".zkey"), os.path.join(d, tag + "_%d.wtns"), meta))
+        subprocess.check_call([sys.executable, "-c", code], stdout=sys.stderr)
+        os.replace(meta + ".tmp", meta)
+    dims = json.load(open(meta))
+    zkey = open(os.path.join(d, tag + ".zkey"), "rb").read()
+    wtns = [open(os.path.join(d, tag + "_%d.wtns" % i), "rb").read() for i in range(n_witness)]
+    return zkey, wtns, dims
+
+
+def config_block(args, world, dims):
+    """`config` of the JSON line -- the SAME keys and values on both arms (the driver compares them)."""
+    return dict(workload="nzcp_%s shape (BASELINE configs[1]), synthetic R1CS + satisfying witnesses" % args.shape,
+                proofs_per_step_per_gpu=args.batch, provers_in_flight=args.provers,
+                parallelism="batch-sharded x%d, no collective" % world,
+                l2="inputs exceed L2: each proof streams the ~5.8 GB expanded proving key (window tables)", **dims)
+
+
 def cpu_reference_proofs(zkey, wtns_list, n_proofs, threads=0):
     """Times the C restatement of snarkjs groth16.prove (oracle/c) on the host: -> (seconds per proof list, info)."""
     from oracle import cref
@@ -120,8 +160,10 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (port: oracle/c) on all host threads."""
     if rank != 0:
         return
-    import torch  # noqa: F401  (GPU only used to generate the synthetic proving key; not timed)
-    zkey, wtns, dims = make_workload(args.shape, 0, 2, 1000)
+    # the synthetic key + witnesses come from a separate process (cached on disk): nothing of nzcp_circom_b200 is
+    # imported or mapped here, the timed region runs oracle/c alone
+    zkey, wtns, dims = make_workload_files(args.shape, 2, 1000)
+    assert "nzcp_circom_b200" not in sys.modules
     for _ in range(args.warmup):
         cpu_reference_proofs(zkey, wtns, 1)
     times, stages, thr, _ = cpu_reference_proofs(zkey, wtns, args.steps)
@@ -131,9 +173,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "groth16_proofs_per_sec", "value": val, "unit": "proofs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u256 (Fr/Fq Montgomery, 4x64-bit limbs)", "data": "synthetic",
-        "config": dict(workload="nzcp_%s shape, synthetic R1CS + witness" % args.shape, proofs_per_step=1, **dims),
+        "config": config_block(args, args.gpus, dims),
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": thr, "kind": "port",
-                         "sample": "%d full proofs (1 per step) of the same workload; C restatement of snarkjs "
+                         "sample": "%d full proofs (ONE per step, not proofs_per_step_per_gpu) of the same workload; C restatement of snarkjs "
                                    "groth16.prove, OpenMP over ffjavascript's task decomposition; NOT snarkjs itself "
                                    "(node absent)" % args.steps,
                          "stage_sec": stages},
@@ -173,6 +215,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--provers", type=int, default=4, help="concurrent provers (host threads + stream sets) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2] / configs[4] records")
+    ap.add_argument("--extras-proofs", type=int, default=1024, help="configs[2]: proofs in the sharded batch")
+    ap.add_argument("--extras-msm-log", type=int, default=24, help="configs[4]: log2 points of the split G1 MSM")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
                     help="library tuning knob (include/nzcp_prover.h nzcp_tuning_set), e.g. prover_rounds_h=0")
     args = ap.parse_args()
@@ -225,8 +270,17 @@ def main():
     host_wtns = [p.numpy() for p in pinned]
 
     def step_e2e(record):
-        # the reference-facing C-ABI call: host .wtns images in, proofs out, the library's own prover threads
-        zk.prove_batch(host_wtns, [R_FIXED] * B, [S_FIXED] * B, n_provers=args.provers)
+        # the reference-facing C-ABI call: host .wtns images in, proofs out, the library's own prover threads, r and s
+        # drawn from the OS CSPRNG per proof exactly as groth16.prove does (None = random)
+        zk.prove_batch(host_wtns, None, None, n_provers=args.provers)
+
+    # the same call from PAGEABLE host memory (what a Node Buffer or a Python bytes object is): the library copies it
+    # through each prover's pinned staging buffer in chunks ("stage_mode" -1); mode 0 hands it to the driver instead
+    import numpy as np
+    pageable = [np.array(p.numpy(), copy=True) for p in pinned]
+
+    def step_e2e_pageable():
+        zk.prove_batch(pageable, None, None, n_provers=args.provers)
 
     def latency_run(count):
         # p50 per-proof latency: one proof at a time through the host-buffer call, nothing else in flight
@@ -257,12 +311,25 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = pr.launch_count()
+    l0 = pool.launch_count()          # per-prover counters, summed over the pool's provers
     ms_dev = timed(step_device, args.steps)
-    launches = pr.launch_count() - l0
+    launches = pool.launch_count() - l0
     ms_e2e = timed(lambda: step_e2e(True), args.steps)
     clocks = sampler.stop()
+    step_e2e_pageable()
+    ms_e2e_pg = timed(step_e2e_pageable, args.steps)
+    api.tuning_set("stage_mode", 0)
+    step_e2e_pageable()
+    ms_e2e_pg_direct = timed(step_e2e_pageable, args.steps)
+    api.tuning_set("stage_mode", -1)
     latency_run(max(8, B))
+    lat_pinned = list(lat)
+    del lat[:]
+    for i in range(max(8, B)):          # lone-proof latency from pageable memory
+        t = time.perf_counter()
+        pr.prove(pageable[i % B], r=R_FIXED, s=S_FIXED)
+        lat.append(time.perf_counter() - t)
+    lat_pageable, lat[:] = list(lat), lat_pinned
 
     # per-stage device times + the dominant kernel, from the library's own CUDA events (one extra proof, not timed above)
     dbg = pr.prove_device(d_wit[0], r=R_FIXED, s=S_FIXED, debug=True)
@@ -278,15 +345,19 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u256 (Fr/Fq Montgomery, 8x32-bit limbs, IMAD.WIDE carry chains)",
             "data": "synthetic",
-            "config": dict(workload="nzcp_%s shape (BASELINE configs[1]), synthetic R1CS + satisfying witnesses" % args.shape,
-                           proofs_per_step_per_gpu=B, provers_in_flight=args.provers, parallelism="batch-sharded x%d, no collective" % world,
-                           l2="inputs exceed L2: each proof streams ~%.0f MB of proving key" % (zk.device_bytes / 1e6),
-                           **dims),
+            "config": config_block(args, world, dims),
             "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": B * m * 32,
                     "d2h_bytes_per_step": B * d2h_per_proof, "ms_per_step": ms_e2e / args.steps,
                     "d2h_note": "per proof: 4 G1 + 1 G2 MSM results as (digits + 1) XYZZ points each + 2 x 32 B of sort flags; "
-                                "the 256-byte proof itself is assembled on the host"},
+                                "the 256-byte proof itself is assembled on the host",
+                    "host_memory": "pinned (cudaHostAlloc) .wtns images, random r/s per proof",
+                    "pageable": {"value": world * B * args.steps / (ms_e2e_pg / 1e3), "unit": "proofs/s",
+                                 "value_driver_staged": world * B * args.steps / (ms_e2e_pg_direct / 1e3),
+                                 "note": "same call with the .wtns images in ordinary pageable memory (a Node Buffer): `value` "
+                                         "= through the prover's pinned staging buffer in 1 MiB chunks (default), "
+                                         "`value_driver_staged` = cudaMemcpyAsync straight from the pageable buffer"}},
             "p50_latency_ms": 1e3 * statistics.median(lat) if lat else None,
+            "p50_latency_ms_pageable": 1e3 * statistics.median(lat_pageable) if lat_pageable else None,
             "gpu_launches": launches, "clocks": clocks, "stage_ms": dbg["stage_ms"],
         }
         if args.tune:
@@ -300,12 +371,126 @@ def main():
                                               "of snarkjs groth16.prove (oracle/c), OpenMP; NOT snarkjs itself",
                                     "stage_sec": stages}
             line["proof_matches_cpu_port"] = correct
+        # one proof of the timed batch through the independent pairing check (CPU, a few seconds)
+        try:
+            from nzcp_circom_b200 import groth16
+            out = pr.prove(host_wtns[0], r=None, s=None)
+            vk = groth16.exportVerificationKey(zkey)
+            line["proof_verifies"] = bool(groth16.verify(vk, groth16._public_signals(host_wtns[0], zk.n_public),
+                                                         groth16.proof_from_bytes(out["proof"])))
+        except Exception as e:  # noqa: BLE001
+            line["proof_verifies"] = "error: %s" % e
+    extra = None
+    if not args.no_extras:
+        try:
+            pool.close()
+            zk.close()
+            extra = run_extras(args, rank, world, local, timed, zkey if args.shape == "example" else None)
+        except Exception as e:  # noqa: BLE001
+            extra = {"error": repr(e)}
+    if rank == 0:
+        if extra is not None:
+            line["extras"] = extra
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if correct is False:
         raise SystemExit("bench.py: GPU proof differs from the CPU port")
+
+
+def run_extras(args, rank, world, local, timed, zkey_example):
+    """The two other multi-GPU configurations of BASELINE.json, recorded as extra keys of the same JSON line so that the
+    driver's --gpus N runs carry them: configs[2] (a fixed batch of nzcp_exampleTest-shape proofs sharded i mod N: STRONG
+    scaling) and configs[4] (one 2^24-point G1 MSM split by point range, NCCL all-gather of the partial sums)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nzcp_circom_b200 import api, parallel
+    out = {}
+    dev = torch.device("cuda", local)
+
+    def agree(ok):
+        """All ranks enter the timed (barrier-bracketed) part of a section, or none does: a rank that failed while
+        preparing must not leave the others waiting in a collective."""
+        if world == 1:
+            return ok
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # ---- configs[2]
+    n_total, n_distinct = args.extras_proofs, 16
+    zk, err = None, None
+    try:
+        nc, npub, nfree = SHAPES["example"]
+        sc = api.SynthCircuit(seed=0xC0FFEE, n_constraints=nc, n_public=npub, n_free=nfree)
+        if zkey_example is None:
+            zkey_example = sc.zkey(TOXIC, device=local)
+        wt = []
+        for i in range(n_distinct):
+            w = sc.wtns(5000 + n_distinct * rank + i)
+            t = torch.empty(len(w), dtype=torch.uint8).pin_memory()
+            t.numpy()[:] = memoryview(w)
+            wt.append(t.numpy())
+        mine = parallel.shard_indices(n_total, rank, world)
+        zk = api.Zkey(zkey_example, device=local)
+        zk.prove_batch([wt[i % n_distinct] for i in range(2 * args.provers)], None, None, n_provers=args.provers)   # warm-up
+    except Exception as e:  # noqa: BLE001
+        err = repr(e)
+    if agree(err is None):
+        ms = timed(lambda: zk.prove_batch([wt[i % n_distinct] for i in mine], None, None, n_provers=args.provers), 1)
+        out["config2_batch"] = {"workload": "nzcp_example shape, %d proofs sharded i mod %d (%d on rank 0; %d distinct witnesses "
+                                            "per rank, cycled; random r/s)" % (n_total, world, len(mine), n_distinct),
+                                "proofs": n_total, "n_gpus": world, "seconds": ms / 1e3, "proofs_per_s": n_total / (ms / 1e3),
+                                "scaling": "strong", "path": "nzcp_prove_batch, pinned host .wtns in, proofs out"}
+    else:
+        out["config2_batch"] = {"error": err or "another rank failed"}
+    if zk is not None:
+        zk.close()
+    del zkey_example
+    # ---- configs[4]
+    log_n = args.extras_msm_log
+    n = 1 << log_n
+    lo, hi = parallel.shard_range(n, rank, world)
+    cnt = hi - lo
+    plan, err, kms = None, None, []
+    mine_t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    try:
+        bases = api.synth_points(1000 + rank, cnt, device=local)
+        sc_np = np.random.RandomState(rank).randint(0, 2 ** 32, size=(cnt, 8), dtype=np.uint64).astype(np.uint32)
+        sc_np[:, 7] &= 0x1FFFFFFF
+        plan = api.MsmPlan(bases, cnt, mode=1, device=local)
+        kms.append(plan.run_partial(sc_np, mine_t))       # warm-up
+    except Exception as e:  # noqa: BLE001
+        err = repr(e)
+    if agree(err is None):
+        def run():
+            kms.append(plan.run_partial(sc_np, mine_t))
+            if world > 1:
+                parts = [torch.empty_like(mine_t) for _ in range(world)]
+                dist.all_gather(parts, mine_t)
+            else:
+                parts = [mine_t]
+            run.result = api.msm_sum_partials(torch.cat(parts), world, device=local)
+        run()
+        ms = timed(run, 2) / 2
+        k = torch.tensor([min(kms[1:])], device=dev)
+        if world > 1:
+            dist.all_reduce(k, op=dist.ReduceOp.MAX)
+        out["config4_split_msm"] = {
+            "workload": "one 2^%d-point G1 MSM, uniform 253-bit scalars, points range-partitioned over %d GPU(s)" % (log_n, world),
+            "n_gpus": world, "points_per_gpu": cnt, "ms": ms, "kernel_ms_max_over_ranks": float(k.item()),
+            "Mpoints_per_s": n / ms / 1e3, "plan_build_ms": plan.build_ms,
+            "path": "per rank: variable-base plan (bases resident, no window table), scalars uploaded from pageable host memory "
+                    "inside the timed region, partial sum left in HBM as one XYZZ point; one all-gather of 128 B per rank over "
+                    "NCCL from and into device memory; nzcp_msm_sum_partials adds them on the GPU",
+            "result_x_low64": int.from_bytes(run.result[:8], "little")}
+    else:
+        out["config4_split_msm"] = {"error": err or "another rank failed"}
+    if plan is not None:
+        plan.close()
+    return out
 
 
 def roofline_block(dbg, zk, hbm, peak_src):
@@ -330,6 +515,9 @@ def roofline_block(dbg, zk, hbm, peak_src):
             "kernel": "msm_accumulate_kernel<Fq> (H MSM bucket accumulation)", "bound": "int32-mul-pipe",
             "achieved": ach / 1e9, "peak": peak_mul / 1e9, "unit": "GFqmul/s", "frac": ach / peak_mul,
             "traffic": 2.29e9 * ent / 16776933.0,
+            "traffic_source": "recorded, not live: dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed "
+                              "ncu --set full capture profiles/r01_ncu_accumulate_ntt_full.md (2.29 GB at 16 776 933 entries), "
+                              "scaled by this run's entry count",
             "launch_ms": acc_ms, "algorithmic_fq_mul": ent * 10,
             "traffic_note": "ncu --set full (profiles/r01_ncu_accumulate_ntt_full.md): dram read+write 2.29 GB per launch vs "
                             "1.14 GB algorithmic (68 B/entry): 64-B points fetched as 128-B lines; DRAM at 10 % of peak, "

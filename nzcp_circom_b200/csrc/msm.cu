@@ -730,29 +730,35 @@ msm_marginal_kernel(const XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ m
   }
 }
 
-// sum_g 2^(c g) * (T_g + sum_k 32^k S_{g,k}) on the device (one warp; lane g folds group g, then a shuffle tree applies
-// the 2^(c g) factors by repeated doubling).  The prover finishes on the host instead (a dozen group operations are
-// faster there); this kernel exists for results that must stay in HBM: the per-rank partial sums of a split MSM.
+// sum_g 2^(c g) * (T_g + sum_k 32^k S_{g,k}) on the device (one warp; lane l folds the groups [l G, (l+1) G) by Horner,
+// G = ceil(n_groups / 32), then a shuffle tree applies the 2^(c G off) factors by repeated doubling).  The prover finishes
+// on the host instead (a dozen group operations are faster there); this kernel exists for results that must stay in
+// HBM: the per-rank partial sums of a split MSM.
 template <class F>
 __global__ void __launch_bounds__(32)
 msm_finish_kernel(const XYZZ<F>* __restrict__ out, XYZZ<F>* __restrict__ result, uint32_t n_groups, uint32_t n_digits, int c) {
   const uint32_t lane = threadIdx.x;
+  const uint32_t per = (n_groups + 31) / 32;
   XYZZ<F> acc = XYZZ<F>::inf();
-  if (lane < n_groups) {
-    const XYZZ<F>* w = out + lane * (n_digits + 1);
+  for (int g = (int)((lane + 1) * per) - 1; g >= (int)(lane * per); g--) {
+    if (!acc.is_inf())
+      for (int d = 0; d < c; d++) acc = xyzz_dbl(acc);
+    if ((uint32_t)g >= n_groups) continue;
+    const XYZZ<F>* w = out + (size_t)g * (n_digits + 1);
+    XYZZ<F> r = XYZZ<F>::inf();
     for (int k = (int)n_digits - 1; k >= 0; k--) {
-      if (!acc.is_inf())
-        for (int d = 0; d < 5; d++) acc = xyzz_dbl(acc);
-      xyzz_add(acc, w[k]);
+      if (!r.is_inf())
+        for (int d = 0; d < 5; d++) r = xyzz_dbl(r);
+      xyzz_add(r, w[k]);
     }
-    xyzz_add(acc, w[n_digits]);
+    xyzz_add(r, w[n_digits]);
+    xyzz_add(acc, r);
   }
-  // tree: acc[l] += 2^(c * off) * acc[l + off]
+  // tree: acc[l] += 2^(c * per * off) * acc[l + off]
   for (uint32_t off = 1; off < 32; off <<= 1) {
     XYZZ<F> o = shfl_down_obj(acc, off);
-    if ((lane & (2 * off - 1)) == 0 && lane + off < n_groups) {
-      for (uint32_t d = 0; d < (uint32_t)c * off; d++)
-        if (!o.is_inf()) o = xyzz_dbl(o);
+    if ((lane & (2 * off - 1)) == 0 && (lane + off) * per < n_groups && !o.is_inf()) {
+      for (uint32_t d = 0; d < (uint32_t)c * per * off; d++) o = xyzz_dbl(o);
       xyzz_add(acc, o);
     }
   }

@@ -16,8 +16,11 @@ The Python functions are synchronous (snarkjs returns Promises); the Node wrappe
 The proving key is parsed and uploaded on first use and cached per (source, device): snarkjs re-reads the five point
 sections from disk on every call.
 """
+import collections
+import hashlib
 import os
 import struct
+import threading
 
 from . import _lib, api, verifier
 from ._lib import NzcpError
@@ -25,36 +28,88 @@ from ._lib import NzcpError
 _Q = verifier.Q
 _RINV_Q = pow(1 << 256, -1, _Q)
 
-_cache = {}          # key -> (Zkey, Prover, vk-source bytes-like)
+MAX_CACHED_KEYS = 4      # resident proving keys kept by prove() (an NZCP key is ~5.8 GB of HBM); least recently used goes
+
+
+class _Entry:
+    """One resident proving key with its prover.  `lock` serialises proofs: an nzcp_prover carries ONE in-flight proof
+    (one stream set, one set of work buffers) and ctypes drops the GIL inside nzcp_prove, so two threads calling
+    groth16.prove on the same key must not reach the library at the same time."""
+
+    def __init__(self, zk, pr):
+        self.zk, self.pr = zk, pr
+        self.lock = threading.Lock()
+
+    def close(self):
+        with self.lock:
+            self.pr.close()
+            self.zk.close()
+
+
+_cache = collections.OrderedDict()     # key -> _Entry, in least-recently-used order
+_cache_lock = threading.Lock()         # guards _cache and makes "load the key once" atomic
 
 
 def _cache_key(zkey, device):
+    """Files are identified by path + mtime + size; in-memory keys by a digest of their CONTENT (an id()-based key
+    would go stale when a bytearray is mutated or an address reused)."""
     if isinstance(zkey, dict) and zkey.get("type") == "mem":
         zkey = zkey["data"]
     if isinstance(zkey, str) or hasattr(zkey, "__fspath__"):
         p = os.path.abspath(os.fspath(zkey))
         st = os.stat(p)
         return ("path", p, st.st_mtime_ns, st.st_size, device)
-    return ("mem", id(zkey), len(zkey), device)
+    return ("mem", _fingerprint(zkey), len(zkey), device)
 
 
-def _get_prover(zkey, device):
+def _fingerprint(buf):
+    """Digest of an in-memory key: everything up to 8 MB; beyond that the first and last 64 KB (header, verification-key
+    points, section table) plus 256 evenly spaced 4 KB blocks -- two different proving keys differ in delta and hence in
+    every C and H point, so sampled blocks tell them apart at ~1 MB hashed per call instead of 0.5 GB."""
+    mv = memoryview(buf).cast("B")
+    n = len(mv)
+    h = hashlib.blake2b(digest_size=16)
+    h.update(n.to_bytes(8, "little"))
+    if n <= (8 << 20):
+        h.update(mv)
+    else:
+        h.update(mv[:65536])
+        h.update(mv[n - 65536:])
+        step = n // 256
+        for k in range(256):
+            h.update(mv[k * step:k * step + 4096])
+    return h.digest()
+
+
+def _get_entry(zkey, device):
     key = _cache_key(zkey, device)
-    ent = _cache.get(key)
-    if ent is None:
-        data = api._as_bytes_like(zkey)
-        zk = api.Zkey(data, device)
-        ent = (zk, api.Prover(zk), zkey if key[0] == "mem" else None)   # keep in-memory sources alive (id() reuse)
-        _cache[key] = ent
-    return ent[0], ent[1]
+    evicted = []
+    with _cache_lock:
+        ent = _cache.get(key)
+        if ent is None:
+            zk = api.Zkey(api._as_bytes_like(zkey), device)      # under the lock: a first-call race must not load it twice
+            try:
+                ent = _Entry(zk, api.Prover(zk))
+            except Exception:
+                zk.close()
+                raise
+            _cache[key] = ent
+            while len(_cache) > MAX_CACHED_KEYS:
+                evicted.append(_cache.popitem(last=False)[1])
+        else:
+            _cache.move_to_end(key)
+    for e in evicted:
+        e.close()          # waits for a proof still running on the evicted key
+    return ent
 
 
 def terminate():
     """snarkjs callers `await curve.terminate()` to stop the worker pool; here it frees the cached GPU state."""
-    for zk, pr, _ in _cache.values():
-        pr.close()
-        zk.close()
-    _cache.clear()
+    with _cache_lock:
+        ents = list(_cache.values())
+        _cache.clear()
+    for e in ents:
+        e.close()
 
 
 def _le(b, i):
@@ -64,13 +119,14 @@ def _le(b, i):
 def proof_from_bytes(pb):
     """256-byte C-ABI proof -> snarkjs proof object (decimal strings of plain affine coordinates)."""
     v = [_le(pb, i) for i in range(8)]
-    a_inf = v[0] == 0 and v[1] == 0
+    # the point at infinity: ffjavascript's G.zero is [0, 1, 0], and that is what toObject(toAffine(P)) prints
+    def g1(x, y):
+        return ["0", "1", "0"] if x == 0 and y == 0 else [str(x), str(y), "1"]
     b_inf = all(x == 0 for x in v[2:6])
-    c_inf = v[6] == 0 and v[7] == 0
     return {
-        "pi_a": [str(v[0]), str(v[1]), "0" if a_inf else "1"],
-        "pi_b": [[str(v[2]), str(v[3])], [str(v[4]), str(v[5])], ["0", "0"] if b_inf else ["1", "0"]],
-        "pi_c": [str(v[6]), str(v[7]), "0" if c_inf else "1"],
+        "pi_a": g1(v[0], v[1]),
+        "pi_b": [["0", "0"], ["1", "0"], ["0", "0"]] if b_inf else [[str(v[2]), str(v[3])], [str(v[4]), str(v[5])], ["1", "0"]],
+        "pi_c": g1(v[6], v[7]),
         "protocol": "groth16",
         "curve": "bn128",
     }
@@ -97,8 +153,10 @@ def prove(zkeyFileName, witnessFileName, logger=None, *, r=None, s=None, device=
     wt = api._as_bytes_like(witnessFileName)
     if logger:
         logger.debug("Reading zkey")
-    zk, pr = _get_prover(zkeyFileName, device)
-    res = pr.prove(wt, r=r, s=s, debug=logger is not None)
+    ent = _get_entry(zkeyFileName, device)
+    zk = ent.zk
+    with ent.lock:
+        res = ent.pr.prove(wt, r=r, s=s, debug=logger is not None)
     if logger:
         for k, v in res["stage_ms"].items():
             logger.debug("%s: %.3f ms" % (k, v))
@@ -148,12 +206,13 @@ def exportVerificationKey(zkeyFileName):
 
     def g1(off):
         x, y = fq(off), fq(off + 32)
-        return [str(x), str(y), "0" if x == 0 and y == 0 else "1"]
+        return ["0", "1", "0"] if x == 0 and y == 0 else [str(x), str(y), "1"]
 
     def g2(off):
         c = [fq(off + 32 * i) for i in range(4)]
-        inf = all(v == 0 for v in c)
-        return [[str(c[0]), str(c[1])], [str(c[2]), str(c[3])], ["0", "0"] if inf else ["1", "0"]]
+        if all(v == 0 for v in c):
+            return [["0", "0"], ["1", "0"], ["0", "0"]]
+        return [[str(c[0]), str(c[1])], [str(c[2]), str(c[3])], ["1", "0"]]
 
     p = h + 84
     vk = {"protocol": "groth16", "curve": "bn128", "nPublic": n_public}

@@ -235,20 +235,82 @@ def pairing_product_is_one(pairs):
 
 
 # ---------------------------------------------------------------------------------------- snarkjs-shaped verify
+class _BadPoint(ValueError):
+    pass
+
+
+def _coord(v):
+    """Canonical field element: a decimal string / int in [0, Q).  Anything else is rejected, never reduced."""
+    x = int(v)
+    if not 0 <= x < Q:
+        raise _BadPoint("coordinate not in [0, q)")
+    return x
+
+
 def _g1(obj):
-    x, y, z = (int(v) for v in obj)
-    return None if z == 0 else (x % Q, y % Q)
+    """snarkjs point object [x, y, z] with z in {"0", "1"} (affine; ffjavascript's zero is ["0", "1", "0"])."""
+    x, y, z = (_coord(v) for v in obj)
+    if z == 0:
+        return None
+    if z != 1:
+        raise _BadPoint("G1 point is not affine")
+    return (x, y)
 
 
 def _g2(obj):
-    (x0, x1), (y0, y1), (z0, z1) = ((int(a), int(b)) for a, b in obj)
-    return None if (z0 == 0 and z1 == 0) else ((x0 % Q, x1 % Q), (y0 % Q, y1 % Q))
+    (x0, x1), (y0, y1), (z0, z1) = ((_coord(a), _coord(b)) for a, b in obj)
+    if z0 == 0 and z1 == 0:
+        return None
+    if (z0, z1) != (1, 0):
+        raise _BadPoint("G2 point is not affine")
+    return ((x0, x1), (y0, y1))
+
+
+def g2_in_subgroup(Pt):
+    """r * P == O.  The twist E'(Fq2) has order r * (2q - r): a point on the curve is not automatically in G2, and the
+    optimal-ate Miller loop is only a pairing on the r-torsion (the invalid-point surface EIP-197 and arkworks close)."""
+    return Pt is None or g2_mul(Pt, R) is None
+
+
+_vk_ok = {}     # content fingerprint of a verification key -> checked once (points on curve, G2 points in the subgroup)
+
+
+def _check_vk(vk):
+    try:
+        key = hash(repr((vk["vk_alpha_1"], vk["vk_beta_2"], vk["vk_gamma_2"], vk["vk_delta_2"], vk["IC"])))
+    except (KeyError, TypeError):
+        return False
+    ent = _vk_ok.get(key)
+    if ent is not None:
+        return ent
+    try:
+        ic = [_g1(p) for p in vk["IC"]]
+        a1 = _g1(vk["vk_alpha_1"])
+        g2s = [_g2(vk[k]) for k in ("vk_beta_2", "vk_gamma_2", "vk_delta_2")]
+        ok = all(g1_on_curve(p) for p in ic + [a1]) and a1 is not None and \
+            all(p is not None and g2_on_curve(p) and g2_in_subgroup(p) for p in g2s)
+    except (_BadPoint, ValueError, TypeError, KeyError):
+        ok = False
+    if len(_vk_ok) > 64:
+        _vk_ok.clear()
+    _vk_ok[key] = ok
+    return ok
 
 
 def verify(vk, public_signals, proof, logger=None):
-    """snarkjs groth16.verify(vk_verifier, publicSignals, proof) -> bool."""
+    """snarkjs groth16.verify(vk_verifier, publicSignals, proof) -> bool.
+
+    Stricter than snarkjs 0.4.12 on malformed input (which it never checks): coordinates must be canonical (< q, not
+    silently reduced), points affine and on the curve, pi_b (and the key's G2 points) in the order-r subgroup."""
+    if not _check_vk(vk):
+        if logger:
+            logger.error("Invalid verification key")
+        return False
     ic = [_g1(p) for p in vk["IC"]]
-    pubs = [int(s) for s in public_signals]
+    try:
+        pubs = [int(s) for s in public_signals]
+    except (ValueError, TypeError):
+        return False
     if len(pubs) + 1 != len(ic):
         if logger:
             logger.error("Invalid number of public signals")
@@ -258,8 +320,13 @@ def verify(vk, public_signals, proof, logger=None):
             if logger:
                 logger.error("Public input not in field")
             return False
-    A, B, Cc = _g1(proof["pi_a"]), _g2(proof["pi_b"]), _g1(proof["pi_c"])
-    if not (g1_on_curve(A) and g2_on_curve(B) and g1_on_curve(Cc)):
+    try:
+        A, B, Cc = _g1(proof["pi_a"]), _g2(proof["pi_b"]), _g1(proof["pi_c"])
+    except (_BadPoint, ValueError, TypeError, KeyError):
+        if logger:
+            logger.error("Invalid proof point")
+        return False
+    if not (g1_on_curve(A) and g2_on_curve(B) and g1_on_curve(Cc) and g2_in_subgroup(B)):
         if logger:
             logger.error("Invalid proof point")
         return False

@@ -305,3 +305,33 @@ def test_prove_with_pair_rounds_forced(lib, rounds):
     finally:
         for nm in names:
             api.tuning_set(nm, -1)
+
+
+def test_groth16_prove_thread_safety_and_bounded_cache(lib):
+    """groth16.prove keeps ONE prover per resident key: concurrent callers are serialised by the entry's lock (ctypes drops
+    the GIL inside nzcp_prove), a first-call race loads the key once, in-memory keys are identified by content (a mutated
+    bytearray is a different key), and the cache holds at most MAX_CACHED_KEYS keys."""
+    from concurrent.futures import ThreadPoolExecutor
+    groth16.terminate()
+    c = tiny_case(seed=41, n_constraints=1500, n_public=4, n_free=30)
+    zb = bytearray(c["zkey_bytes"])
+    zmem, wmem = {"type": "mem", "data": zb}, {"type": "mem", "data": c["wtns_bytes"]}
+    r, s = 0x55AA55AA, 0x77CC77CC
+    want = oprover.proof_to_json(oprover.prove(formats.read_zkey(c["zkey_bytes"]), c["witness"], r, s)[0])
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        outs = list(ex.map(lambda _: groth16.prove(zmem, wmem, r=r, s=s), range(18)))
+    assert all(o["proof"] == want for o in outs)
+    assert len(groth16._cache) == 1
+    # same object, different content -> a different resident key (here: another circuit's key written into the buffer)
+    c2 = tiny_case(seed=42, n_constraints=1500, n_public=4, n_free=30)
+    assert len(c2["zkey_bytes"]) == len(zb)
+    zb[:] = c2["zkey_bytes"]
+    out2 = groth16.prove(zmem, {"type": "mem", "data": c2["wtns_bytes"]}, r=r, s=s)
+    want2 = oprover.proof_to_json(oprover.prove(formats.read_zkey(c2["zkey_bytes"]), c2["witness"], r, s)[0])
+    assert out2["proof"] == want2 and len(groth16._cache) == 2
+    for seed in range(50, 50 + groth16.MAX_CACHED_KEYS + 1):
+        ck = tiny_case(seed=seed, n_constraints=60, n_public=2, n_free=5)
+        groth16.prove({"type": "mem", "data": ck["zkey_bytes"]}, {"type": "mem", "data": ck["wtns_bytes"]})
+    assert len(groth16._cache) == groth16.MAX_CACHED_KEYS
+    groth16.terminate()
+    assert len(groth16._cache) == 0
