@@ -121,6 +121,16 @@ typedef struct nzcp_zkey_check {
 } nzcp_zkey_check;
 int nzcp_zkey_selfcheck(const uint8_t* bytes, size_t len, int device, nzcp_zkey_check* report);
 
+/* snarkjs `zkey new` (zkey_new.js newZKey(r1csName, ptauName, zkeyName)): the circuit-specific Groth16 key from an .r1cs
+ * (circom --r1cs, /root/reference/Makefile:5-9) and a PREPARED powers-of-tau file (sections 12-15 present;
+ * /root/reference/Makefile:31 names powersOfTau28_hez_final_22.ptau).  gamma = delta = 1 as after `zkey new`; section 10
+ * (circuit hash) is written zero-filled -- see csrc/setup.cu.  Errors carry snarkjs's messages ("Powers of tau is not
+ * prepared.", "circuit too big for this power of tau ceremony. ...", "r1cs curve does not match powers of tau ceremony
+ * curve").  The sparse point combinations run on `device`. */
+int nzcp_zkey_new_size(const uint8_t* r1cs, size_t r1cs_len, const uint8_t* ptau, size_t ptau_len, size_t* out_size);
+int nzcp_zkey_new(const uint8_t* r1cs, size_t r1cs_len, const uint8_t* ptau, size_t ptau_len, int device, uint8_t* out,
+                  size_t cap, size_t* written);
+
 /* Work buffers + streams for proofs against `zk`.  Several provers may share one zkey (one per host thread). */
 int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out);
 void nzcp_prover_free(nzcp_prover* p);
@@ -186,7 +196,10 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
  *   "pair_k1" / "pair_k2" / "pair_k3"  additions per thread in round 1 / 2 / 3: 4, 8, 16 or 32
  *   "stage_mode"  host witness upload in nzcp_prove*: -1 = automatic (pageable memory through the prover's pinned staging
  *                 buffer in chunks, caller-pinned memory directly), 0 = always direct, 1 = always staged
- *   "stage_chunk_kb"  staging chunk size in KiB (default 1024) */
+ *   "stage_chunk_kb"  staging chunk size in KiB (default 1024)
+ *   "prover_c_h" / "prover_c_w"  window bits of the H / witness MSM tables, read by nzcp_zkey_load (0 = default: 16 at 2^20)
+ *   "ntt_tma"     1 (default) = TMA-staged low NTT pass (bulk copies + mbarrier, twiddles in shared memory), 0 = thread-loaded
+ *   "stage_threads"   host threads sharing the copy into the staging buffer (default 4; 1 = the calling thread alone) */
 int nzcp_tuning_set(const char* name, int value);
 
 /* Integer-pipe microbenchmark (the MSM / NTT roofline denominator): out[0] = IMAD.WIDE.U32 (32x32->64 multiply-add) per

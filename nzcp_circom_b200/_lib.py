@@ -71,6 +71,8 @@ SIGNATURES = {
     "nzcp_ntt_coset": (C.c_int, [_U8P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "nzcp_msm": (C.c_int, [_U8P, _U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, _U8P, C.POINTER(C.c_float)]),
     "nzcp_zkey_selfcheck": (C.c_int, [_U8P, C.c_size_t, C.c_int, C.POINTER(ZkeyCheck)]),
+    "nzcp_zkey_new_size": (C.c_int, [_U8P, C.c_size_t, _U8P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "nzcp_zkey_new": (C.c_int, [_U8P, C.c_size_t, _U8P, C.c_size_t, C.c_int, _U8P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nzcp_msm_plan_create": (C.c_int, [_U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P),
                                        C.POINTER(C.c_float)]),
     "nzcp_msm_plan_free": (None, [_P]),

@@ -313,6 +313,20 @@ def msm_sum_partials(d_partials, count, g2=False, device=0):
     return bytes(out)
 
 
+def zkey_new(r1cs, ptau, device=0):
+    """snarkjs `zkey new`: .r1cs + prepared .ptau (path | bytes-like | {"type": "mem"}) -> bytearray with the .zkey image
+    (gamma = delta = 1, no contributions).  The sparse point combinations run on `device` (csrc/setup.cu)."""
+    lib = _lib.load()
+    rb, pb = _as_bytes_like(r1cs), _as_bytes_like(ptau)
+    size = C.c_size_t()
+    check(lib.nzcp_zkey_new_size(addr(rb), _nbytes(rb), addr(pb), _nbytes(pb), C.byref(size)))
+    out = bytearray(size.value)
+    written = C.c_size_t()
+    check(lib.nzcp_zkey_new(addr(rb), _nbytes(rb), addr(pb), _nbytes(pb), int(device), addr(out), len(out), C.byref(written)))
+    assert written.value == len(out)
+    return out
+
+
 def zkey_selfcheck(zkey, device=0):
     """Format self-checks of SURVEY.md 8c-3 on a .zkey image (path | bytes-like | {"type": "mem"}) -> dict; ["ok"] is
     the verdict.  Meant for the first REAL snarkjs-made key: it pins the section-4 `coef * R^2` convention, the moduli

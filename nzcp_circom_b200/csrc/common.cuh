@@ -48,6 +48,8 @@ struct NttDomain {
   Fr* tw_inv = nullptr;   // w^-j
   Fr* coset_scale = nullptr;  // n^-1 * inc^bitrev(p), p < n   (iNTT scale fused with batchApplyKey)
   Fr* ninv_scale = nullptr;   // unused slot kept for standalone iNTT: single element n^-1 (device)
+  unsigned char* tw_lo_fwd = nullptr;   // log_n >= 10: w^(j n/1024), j < 512, padded layout (ntt.cu tw_pad_off): the twiddles
+  unsigned char* tw_lo_inv = nullptr;   // of every stage of a 2^10 tile, bulk-copied into shared memory by the low pass
 };
 void ntt_domain_create(NttDomain* d, int log_n, cudaStream_t st);
 void ntt_domain_destroy(NttDomain* d);

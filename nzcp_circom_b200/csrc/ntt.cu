@@ -25,6 +25,7 @@ static constexpr int kNttThreads = 256;
 #define NZCP_NTT_MIN_BLOCKS 2
 #endif
 static constexpr int kMaxPassBits = 10;
+std::atomic<int> g_tune_ntt_tma{1};   // "ntt_tma" knob: 1 = TMA-staged low pass (below), 0 = the thread-loaded one
 
 __device__ __forceinline__ uint32_t pad_idx(uint32_t l) { return l + (l >> 5); }
 
@@ -212,6 +213,167 @@ ntt_fused_lo_kernel(Fr* __restrict__ data, const Fr* __restrict__ tw_inv, const 
   for (uint32_t l = threadIdx.x; l < tile_elems; l += blockDim.x) g_store(x + base + l, sm_load(sm, plane, l));
 }
 
+
+// ------------------------------------------------------------------------------------------------ TMA-staged low pass
+// The same low pass with its operands staged by the copy engine instead of by the threads (north_star: "TMA-staged,
+// coalesced 128-bit HBM access"):
+//   * persistent blocks (two per SM) walk the contiguous 32 KB tiles of all polynomials; while a tile is being transformed
+//     the NEXT one is already in flight: one 1-D bulk copy (cp.async.bulk.shared::cluster.global, SASS UBLKCP) into a
+//     staging buffer, completion counted in bytes on an mbarrier -- no thread issues a load for the data it will touch;
+//   * the twiddles of the pass -- 512 of each direction, w^(j * n/1024): every stage of a 2^10-point tile draws from this
+//     set -- are bulk-copied ONCE per block into shared memory and read from there in the butterflies, instead of one
+//     L2 round trip per butterfly (ncu r01: long_scoreboard 1.1-1.5 in this kernel, all of it twiddle fetches).
+// The staging buffer is array-of-structures (what a linear copy lands); one repack pass moves it into the limb-planar,
+// padded compute tile (same 10 shared-memory instructions per element the direct global->shared load used to cost).
+// The compact twiddle tables are stored PADDED in global memory (16 B after every 4 and every 32 entries), so that the
+// power-of-two strides of the radix-4 sweeps are bank-conflict free for 128-bit shared loads; the bulk copy lands the
+// padded layout as is.
+static constexpr int kLoTmaBits = 10;
+static constexpr uint32_t kLoTmaTile = 1u << kLoTmaBits;
+static constexpr uint32_t kLoTmaTileBytes = kLoTmaTile * 32;
+static constexpr uint32_t kLoTwEntries = kLoTmaTile / 2;
+__host__ __device__ constexpr uint32_t tw_pad_off(uint32_t j) { return 32 * j + 16 * (j >> 2) + 16 * (j >> 5); }
+static constexpr uint32_t kLoTwBytes = tw_pad_off(kLoTwEntries);   // 18 688
+static constexpr uint32_t kLoPlane = kLoTmaTile + (kLoTmaTile >> 5) + 1;
+static constexpr uint32_t kLoTmaSmem = kLoTmaTileBytes + 8 * kLoPlane * 4 + 2 * kLoTwBytes + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (bytes a multiple of 16, both addresses 16-byte aligned), completing on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ Fr lds_fr(const unsigned char* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ Fr tw_sm(const unsigned char* tw, uint32_t j) { return lds_fr(tw + tw_pad_off(j)); }
+
+// Stages sl and sl + 1 of the contiguous 2^10 tile (global bit = local bit), twiddles from the padded shared table:
+// w^(imod * n / 2^(s+1)) = table[imod << (9 - s)].
+template <bool DIT>
+__device__ __forceinline__ void lo_stage4(uint32_t* sm, const unsigned char* tw, int sl) {
+  for (uint32_t g = threadIdx.x; g < (kLoTmaTile >> 2); g += blockDim.x) {
+    const uint32_t l00 = ((g >> sl) << (sl + 2)) | (g & ((1u << sl) - 1));
+    const uint32_t l01 = l00 | (1u << sl), l10 = l00 | (2u << sl), l11 = l00 | (3u << sl);
+    const uint32_t imod = l00 & ((1u << sl) - 1);
+    const uint32_t j1 = imod << (9 - sl), j2 = imod << (8 - sl), j3 = j2 + (kLoTwEntries >> 1);
+    Fr x0 = sm_load(sm, kLoPlane, l00), x1 = sm_load(sm, kLoPlane, l01);
+    Fr x2 = sm_load(sm, kLoPlane, l10), x3 = sm_load(sm, kLoPlane, l11);
+    if (DIT) {
+      if (j1) {
+        Fr w1 = tw_sm(tw, j1);
+        x1 = fp_mul(x1, w1);
+        x3 = fp_mul(x3, w1);
+      }
+      Fr s0 = fp_add(x0, x1), s1 = fp_sub(x0, x1), s2 = fp_add(x2, x3), s3 = fp_sub(x2, x3);
+      if (j2) s2 = fp_mul(s2, tw_sm(tw, j2));
+      s3 = fp_mul(s3, tw_sm(tw, j3));
+      sm_store(sm, kLoPlane, l00, fp_add(s0, s2));
+      sm_store(sm, kLoPlane, l10, fp_sub(s0, s2));
+      sm_store(sm, kLoPlane, l01, fp_add(s1, s3));
+      sm_store(sm, kLoPlane, l11, fp_sub(s1, s3));
+    } else {
+      Fr p0 = fp_add(x0, x2), p2 = fp_sub(x0, x2), p1 = fp_add(x1, x3), p3 = fp_sub(x1, x3);
+      if (j2) p2 = fp_mul(p2, tw_sm(tw, j2));
+      p3 = fp_mul(p3, tw_sm(tw, j3));
+      Fr d0 = fp_sub(p0, p1), d1 = fp_sub(p2, p3);
+      if (j1) {
+        Fr w1 = tw_sm(tw, j1);
+        d0 = fp_mul(d0, w1);
+        d1 = fp_mul(d1, w1);
+      }
+      sm_store(sm, kLoPlane, l00, fp_add(p0, p1));
+      sm_store(sm, kLoPlane, l01, d0);
+      sm_store(sm, kLoPlane, l10, fp_add(p2, p3));
+      sm_store(sm, kLoPlane, l11, d1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNttThreads, 2)
+ntt_fused_lo_tma_kernel(Fr* __restrict__ data, const unsigned char* __restrict__ tw_inv_lo,
+                        const unsigned char* __restrict__ tw_fwd_lo, const Fr* __restrict__ scale, int log_n, uint32_t n_tiles) {
+  extern __shared__ __align__(128) unsigned char lo_smem[];
+  unsigned char* stage = lo_smem;                                                     // 32 KB, bulk-copy destination
+  uint32_t* sm = reinterpret_cast<uint32_t*>(lo_smem + kLoTmaTileBytes);             // limb-planar compute tile
+  unsigned char* tw_inv = lo_smem + kLoTmaTileBytes + 8 * kLoPlane * 4;
+  unsigned char* tw_fwd = tw_inv + kLoTwBytes;
+  uint64_t* bar_tile = reinterpret_cast<uint64_t*>(tw_fwd + kLoTwBytes);
+  uint64_t* bar_tw = bar_tile + 1;
+  const uint32_t tile_bits = (uint32_t)(log_n - kLoTmaBits);                         // tiles per polynomial = 2^tile_bits
+  auto tile_ptr = [&](uint32_t t) { return data + (((size_t)(t >> tile_bits)) << log_n) + ((size_t)(t & ((1u << tile_bits) - 1)) << kLoTmaBits); };
+  uint32_t t = blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_tile, 1);
+    mbar_init(bar_tw, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar_tw, 2 * kLoTwBytes);
+    bulk_g2s(tw_inv, tw_inv_lo, kLoTwBytes, bar_tw);
+    bulk_g2s(tw_fwd, tw_fwd_lo, kLoTwBytes, bar_tw);
+    if (t < n_tiles) {
+      mbar_expect_tx(bar_tile, kLoTmaTileBytes);
+      bulk_g2s(stage, tile_ptr(t), kLoTmaTileBytes, bar_tile);
+    }
+  }
+  __syncthreads();                 // barrier initialisation visible to every waiter
+  mbar_wait(bar_tw, 0);
+  uint32_t parity = 0;
+  for (; t < n_tiles; t += gridDim.x) {
+    mbar_wait(bar_tile, parity);
+    parity ^= 1;
+    for (uint32_t l = threadIdx.x; l < kLoTmaTile; l += blockDim.x) sm_store(sm, kLoPlane, l, lds_fr(stage + 32 * l));
+    __syncthreads();               // staging buffer drained, compute tile complete
+    const uint32_t tn = t + gridDim.x;
+    if (threadIdx.x == 0 && tn < n_tiles) {   // next tile on its way while this one is transformed
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar_tile, kLoTmaTileBytes);
+      bulk_g2s(stage, tile_ptr(tn), kLoTmaTileBytes, bar_tile);
+    }
+    for (int sl = kLoTmaBits - 2; sl >= 0; sl -= 2) {      // DIF: stages 9..0, two at a time
+      lo_stage4<false>(sm, tw_inv, sl);
+      __syncthreads();
+    }
+    Fr* x = tile_ptr(t);
+    const Fr* sc = scale + ((size_t)(t & ((1u << tile_bits) - 1)) << kLoTmaBits);
+    for (uint32_t l = threadIdx.x; l < kLoTmaTile; l += blockDim.x) {
+      Fr v = sm_load(sm, kLoPlane, l);
+      sm_store(sm, kLoPlane, l, fp_mul(v, g_load(sc + l)));
+    }
+    __syncthreads();
+    for (int sl = 0; sl < kLoTmaBits; sl += 2) {           // DIT: stages 0..9
+      lo_stage4<true>(sm, tw_fwd, sl);
+      __syncthreads();
+    }
+    for (uint32_t l = threadIdx.x; l < kLoTmaTile; l += blockDim.x) g_store(x + l, sm_load(sm, kLoPlane, l));
+    __syncthreads();               // compute tile free for the next repack
+  }
+}
+
 __global__ void bitrev_permute_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, int log_n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ((size_t)1 << log_n)) return;
@@ -269,6 +431,7 @@ static void ensure_smem_attrs() {
   NZCP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   NZCP_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   NZCP_CUDA(cudaFuncSetAttribute(ntt_fused_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  NZCP_CUDA(cudaFuncSetAttribute(ntt_fused_lo_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoTmaSmem));
 }
 
 void ntt_domain_create(NttDomain* d, int log_n, cudaStream_t st) {
@@ -295,6 +458,17 @@ void ntt_domain_create(NttDomain* d, int log_n, cudaStream_t st) {
     scale[p] = k;
     k = fp_mul(k, inc);
   }
+  if (log_n >= kLoTmaBits) {   // compact, padded twiddle tables of the TMA-staged low pass: entry j = w^(+-j * n / 1024)
+    std::vector<unsigned char> pf(kLoTwBytes, 0), pi(kLoTwBytes, 0);
+    for (uint32_t j = 0; j < kLoTwEntries; j++) {
+      memcpy(pf.data() + tw_pad_off(j), &fwd[(size_t)j << (log_n - kLoTmaBits)], sizeof(Fr));
+      memcpy(pi.data() + tw_pad_off(j), &inv[(size_t)j << (log_n - kLoTmaBits)], sizeof(Fr));
+    }
+    NZCP_CUDA(cudaMalloc((void**)&d->tw_lo_fwd, kLoTwBytes));
+    NZCP_CUDA(cudaMalloc((void**)&d->tw_lo_inv, kLoTwBytes));
+    NZCP_CUDA(cudaMemcpy(d->tw_lo_fwd, pf.data(), kLoTwBytes, cudaMemcpyHostToDevice));
+    NZCP_CUDA(cudaMemcpy(d->tw_lo_inv, pi.data(), kLoTwBytes, cudaMemcpyHostToDevice));
+  }
   NZCP_CUDA(cudaMalloc(&d->tw_fwd, (n / 2) * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&d->tw_inv, (n / 2) * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&d->coset_scale, n * sizeof(Fr)));
@@ -311,6 +485,8 @@ void ntt_domain_destroy(NttDomain* d) {
   cudaFree(d->tw_inv);
   cudaFree(d->coset_scale);
   cudaFree(d->ninv_scale);
+  cudaFree(d->tw_lo_fwd);
+  cudaFree(d->tw_lo_inv);
   *d = NttDomain();
 }
 
@@ -346,9 +522,18 @@ void ntt_coset_pipeline(const NttDomain& d, Fr* data, int batch, cudaStream_t st
   auto hp = hi_passes(d.log_n, lo_bits);
   for (int i = (int)hp.size() - 1; i >= 0; i--)
     launch_pass<false>(data, d.tw_inv, d.log_n, hp[i].first, hp[i].second, batch, st);
-  dim3 grid(1u << (d.log_n - lo_bits), batch);
-  ntt_fused_lo_kernel<<<grid, kNttThreads, pass_smem_bytes(lo_bits, 0), st>>>(data, d.tw_inv, d.tw_fwd, d.coset_scale,
-                                                                              d.log_n, lo_bits);
+  if (g_tune_ntt_tma.load() && lo_bits == kLoTmaBits && d.tw_lo_fwd) {
+    const uint32_t n_tiles = (uint32_t)batch << (d.log_n - kLoTmaBits);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t grid_tma = n_tiles < (uint32_t)(2 * sms) ? n_tiles : (uint32_t)(2 * sms);   // persistent: two blocks per SM
+    ntt_fused_lo_tma_kernel<<<grid_tma, kNttThreads, kLoTmaSmem, st>>>(data, d.tw_lo_inv, d.tw_lo_fwd, d.coset_scale, d.log_n,
+                                                                       n_tiles);
+  } else {
+    dim3 grid(1u << (d.log_n - lo_bits), batch);
+    ntt_fused_lo_kernel<<<grid, kNttThreads, pass_smem_bytes(lo_bits, 0), st>>>(data, d.tw_inv, d.tw_fwd, d.coset_scale,
+                                                                                d.log_n, lo_bits);
+  }
   NZCP_LAUNCH_CHECK();
   for (size_t i = 0; i < hp.size(); i++) launch_pass<true>(data, d.tw_fwd, d.log_n, hp[i].first, hp[i].second, batch, st);
 }

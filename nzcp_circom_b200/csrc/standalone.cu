@@ -11,7 +11,9 @@ namespace nzcp {
 extern std::atomic<int> g_tune_rounds;                   // msm.cu
 extern std::atomic<int> g_tune_pair_k[kMsmMaxRounds];
 extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;
-extern std::atomic<int> g_tune_stage_mode, g_tune_stage_chunk_kb;   // prover.cu
+extern std::atomic<int> g_tune_ntt_tma;   // ntt.cu
+extern std::atomic<int> g_tune_c_h, g_tune_c_w;   // prover.cu
+extern std::atomic<int> g_tune_stage_mode, g_tune_stage_chunk_kb, g_tune_stage_threads;   // prover.cu
 
 G1Affine g1_generator();  // synth.cu
 Fr host_fr_root(int k);     // ntt.cu
@@ -713,6 +715,10 @@ int nzcp_tuning_set(const char* name, int value) {
     else if (k == "pair_k3") g_tune_pair_k[2].store(value);
     else if (k == "stage_mode") g_tune_stage_mode.store(value);
     else if (k == "stage_chunk_kb") g_tune_stage_chunk_kb.store(value);
+    else if (k == "stage_threads") g_tune_stage_threads.store(value);
+    else if (k == "ntt_tma") g_tune_ntt_tma.store(value);
+    else if (k == "prover_c_h") g_tune_c_h.store(value);
+    else if (k == "prover_c_w") g_tune_c_w.store(value);
     else throw ApiError(NZCP_E_ARG, "unknown tuning knob: " + k);
   });
 }

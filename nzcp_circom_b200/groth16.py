@@ -5,6 +5,8 @@ yarn.lock:987-999).  The reference's tests build the prover input at /root/refer
 (`{ toBeSigned: bufferToBitArray(bytes), toBeSignedLen }`) and read public signals as witness[1..513] at
 test/nzcp.js:41-48; `publicSignals` below is that same slice, in the same order, as decimal strings.
 
+`zKey` groups newZKey / exportVerificationKey the way snarkjs's main.js does (snarkjs.zKey.newZKey, ...).
+
 Same names, argument meaning and error text as snarkjs:
   prove(zkeyFileName, witnessFileName, logger=None)   file args: path | bytes-like | {"type": "mem", "data": ...}
   fullProve(input, wasmFile, zkeyFileName, logger=None)
@@ -183,6 +185,21 @@ def verify(vk_verifier, publicSignals, proof, logger=None):
     return verifier.verify(vk_verifier, publicSignals, proof, logger)
 
 
+def newZKey(r1csName, ptauName, zkeyName=None, logger=None, *, device=0):
+    """snarkjs zKey.newZKey(r1csName, ptauName, zkeyName): the circuit-specific key from an .r1cs and a prepared .ptau,
+    computed on the GPU.  `zkeyName`: a path to write, a {"type": "mem"} object that receives `.data`, or None.
+    Returns the .zkey image (snarkjs returns the circuit hash, which is not computed here -- csrc/setup.cu)."""
+    if logger:
+        logger.info("Reading r1cs / ptau, combining points on the GPU")
+    data = api.zkey_new(r1csName, ptauName, device=device)
+    if isinstance(zkeyName, dict):
+        zkeyName["data"] = data
+    elif zkeyName is not None:
+        with open(zkeyName, "wb") as f:
+            f.write(data)
+    return data
+
+
 def exportVerificationKey(zkeyFileName):
     """snarkjs zKey.exportVerificationKey: header points + IC (section 3), plain decimal strings."""
     data = api._as_bytes_like(zkeyFileName)
@@ -223,3 +240,9 @@ def exportVerificationKey(zkeyFileName):
     ic0 = secs[3][0]
     vk["IC"] = [g1(ic0 + 64 * i) for i in range(n_public + 1)]
     return vk
+
+
+class zKey:
+    """snarkjs.zKey namespace: the two entries that border the proving path."""
+    newZKey = staticmethod(newZKey)
+    exportVerificationKey = staticmethod(exportVerificationKey)

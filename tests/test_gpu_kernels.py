@@ -90,6 +90,32 @@ def test_ntt_coset_pipeline_vs_oracle(lib, log_n, batch):
         assert got[k * n:(k + 1) * n] == _coset_oracle(p, log_n)
 
 
+@pytest.mark.parametrize("log_n,batch", [(10, 1), (10, 3), (12, 3), (14, 5), (16, 3)])
+def test_ntt_coset_tma_and_thread_loaded_low_pass_agree(lib, log_n, batch):
+    """Both low-pass kernels -- TMA-staged (bulk copies + mbarrier, shared-memory twiddles; persistent blocks that walk
+    several tiles, incl. grids smaller and larger than the tile count) and thread-loaded -- against the C oracle."""
+    import numpy as np
+    from oracle import cref
+    n = 1 << log_n
+    rs = np.random.RandomState(log_n * 7 + batch)
+    x = rs.randint(0, 2 ** 32, size=(batch * n, 8), dtype=np.uint64).astype(np.uint32)
+    x[:, 7] &= 0x1FFFFFFF
+    x[0] = 0
+    exp = x.copy()
+    for k in range(batch):
+        e = np.ascontiguousarray(exp[k * n:(k + 1) * n])
+        cref.ntt_coset(e, log_n, threads=cref.max_threads())
+        exp[k * n:(k + 1) * n] = e
+    try:
+        for tma in (1, 0):
+            api.tuning_set("ntt_tma", tma)
+            g = x.copy()
+            api.ntt_coset(g, log_n, batch=batch)
+            assert np.array_equal(g, exp), "ntt_tma=%d" % tma
+    finally:
+        api.tuning_set("ntt_tma", 1)
+
+
 def test_ntt_roundtrip_large(lib):
     """2^20 (the NZCP domain) and 2^22: forward then inverse is the identity; linearity against a second vector."""
     import numpy as np

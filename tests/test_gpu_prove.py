@@ -322,9 +322,10 @@ def test_groth16_prove_thread_safety_and_bounded_cache(lib):
         outs = list(ex.map(lambda _: groth16.prove(zmem, wmem, r=r, s=s), range(18)))
     assert all(o["proof"] == want for o in outs)
     assert len(groth16._cache) == 1
-    # same object, different content -> a different resident key (here: another circuit's key written into the buffer)
-    c2 = tiny_case(seed=42, n_constraints=1500, n_public=4, n_free=30)
-    assert len(c2["zkey_bytes"]) == len(zb)
+    # same object, different content -> a different resident key (here: the same circuit set up with other toxic waste,
+    # written into the same bytearray; the witness is unchanged)
+    c2 = tiny_case(seed=41, n_constraints=1500, n_public=4, n_free=30, toxic=dict(TOXIC, delta=0xD1FFE7E27, tau=0x7A07A0))
+    assert len(c2["zkey_bytes"]) == len(zb) and c2["zkey_bytes"] != bytes(zb)
     zb[:] = c2["zkey_bytes"]
     out2 = groth16.prove(zmem, {"type": "mem", "data": c2["wtns_bytes"]}, r=r, s=s)
     want2 = oprover.proof_to_json(oprover.prove(formats.read_zkey(c2["zkey_bytes"]), c2["witness"], r, s)[0])
