@@ -244,8 +244,8 @@ def main():
         api.tuning_set(k, int(v))
     zkey, wtns, dims = make_workload(args.shape, local, B, 1 + rank * B)
     zk = api.Zkey(zkey, device=local)
-    pool = api.ProverPool(zk, args.provers)
-    pr = pool.provers[0]
+    pool = api.ProverPool(zk, args.provers)     # throughput-mode provers (what nzcp_prove_batch uses as well)
+    pr = api.Prover(zk)                         # latency-mode prover: p50 of a lone proof, per-kernel timings
     m = zk.n_vars
 
     # host side: .wtns images in pinned memory (what the N-API shim hands over); device side: resident witnesses
@@ -363,6 +363,9 @@ def main():
         if args.tune:
             line["config"]["tune"] = args.tune
         line.update(roofline_block(dbg, zk, hbm, peak_src))
+        line["roofline_step"] = step_roofline(dbg, zk, value / world, line["roofline"]["peak"] if "roofline" in line else None)
+        line["modes"] = ("value / e2e: %d throughput-mode provers in flight (batched-affine pair rounds on); "
+                                   "p50_latency_ms, stage_ms, roofline: one latency-mode prover, lone proofs" % args.provers)
         if not args.no_cpu_baseline:
             times, stages, thr, cproof = cpu_reference_proofs(zkey, wtns, 1)
             correct = (cproof == dbg["proof"])
@@ -384,6 +387,7 @@ def main():
     if not args.no_extras:
         try:
             pool.close()
+            pr.close()
             zk.close()
             extra = run_extras(args, rank, world, local, timed, zkey if args.shape == "example" else None)
         except Exception as e:  # noqa: BLE001
@@ -490,6 +494,34 @@ def run_extras(args, rank, world, local, timed, zkey_example):
         out["config4_split_msm"] = {"error": err or "another rank failed"}
     if plan is not None:
         plan.close()
+    return out
+
+
+def step_roofline(dbg, zk, proofs_per_s_per_gpu, peak_gmul):
+    """The whole proving step against the integer-pipe roofline: CANONICAL field products per proof (signed
+    c = 16 Pippenger, 10 / 28 Fq products per G1 / G2 bucket addition, per-window bucket reduction 16 x 2 x 2^15 full
+    additions at 14 / 40; NTT (n/2) log n per transform; one product per R1CS coefficient and per join element) times the
+    measured proofs/s of ONE GPU, over the measured IMAD.WIDE peak / 128.  An implementation that executes fewer products
+    (window tables: one bucket set instead of 16; batched-affine additions) is still scored against the canonical count,
+    so the fraction may exceed the per-kernel ones."""
+    if not peak_gmul:
+        return None
+    ew, eh = dbg["n_entries"]["witness"], dbg["n_entries"]["h"]
+    n = zk.domain_size
+    lg = n.bit_length() - 1
+    acc = eh * 10 + 3 * ew * 10 + ew * 28
+    red = 16 * 2 * (1 << 15) * (4 * 14 + 40)
+    ntt = 6 * (n // 2) * lg + 3 * n
+    rest = zk.n_coefs + n + 2 * n
+    tot = acc + red + ntt + rest
+    out = {"bound": "int32-mul-pipe", "unit": "GFqmul/s", "peak": peak_gmul,
+           "canonical_fq_mul_per_proof": {"bucket_additions": acc, "per_window_bucket_reduction": red, "ntt": ntt,
+                                          "r1cs_and_join": rest, "total": tot},
+           "achieved": tot * proofs_per_s_per_gpu / 1e9, "frac": tot * proofs_per_s_per_gpu / 1e9 / peak_gmul,
+           "achieved_without_reduction_term": (tot - red) * proofs_per_s_per_gpu / 1e9,
+           "frac_without_reduction_term": (tot - red) * proofs_per_s_per_gpu / 1e9 / peak_gmul,
+           "note": "per GPU, from `value`; measured pipe occupancy of the same step (ncu, sum of duration x fmaheavy-active "
+                   "over one proof's launches / ms per proof): profiles/r02_pipe_summary.txt"}
     return out
 
 

@@ -132,7 +132,11 @@ int nzcp_zkey_new(const uint8_t* r1cs, size_t r1cs_len, const uint8_t* ptau, siz
                   size_t cap, size_t* written);
 
 /* Work buffers + streams for proofs against `zk`.  Several provers may share one zkey (one per host thread). */
-int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out);
+int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out);   /* = mode 0 */
+/* mode 0 = latency (one proof at a time, lowest per-proof latency), mode 1 = throughput (meant to run beside other provers
+ * on the same GPU: bucket accumulation goes through batched-affine pair rounds, +5 % proofs/s, +0.45 ms per lone proof,
+ * ~6 GB more scratch).  nzcp_prove_batch uses throughput-mode provers.  Same proofs, bit for bit, in both modes. */
+int nzcp_prover_create_mode(nzcp_zkey* zk, int mode, nzcp_prover** out);
 void nzcp_prover_free(nzcp_prover* p);
 
 /* groth16.prove: `wtns` is a complete .wtns file image.  r, s: 32-byte LE blinding scalars (< r); NULL draws them

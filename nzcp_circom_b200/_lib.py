@@ -59,6 +59,7 @@ SIGNATURES = {
     "nzcp_zkey_info_get": (C.c_int, [_P, C.POINTER(ZkeyInfo)]),
     "nzcp_zkey_free": (None, [_P]),
     "nzcp_prover_create": (C.c_int, [_P, C.POINTER(_P)]),
+    "nzcp_prover_create_mode": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "nzcp_prover_free": (None, [_P]),
     "nzcp_prove": (C.c_int, [_P, _U8P, C.c_size_t, _U8P, _U8P, C.POINTER(Proof), C.POINTER(ProveDebug)]),
     "nzcp_prove_batch": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, _U8P, _U8P,

@@ -99,10 +99,12 @@ class Zkey:
 class Prover:
     """Work buffers + streams for proofs against one Zkey.  One in-flight proof per Prover."""
 
-    def __init__(self, zkey):
+    def __init__(self, zkey, throughput=False):
+        """throughput=False: latency mode (a lone proof at a time).  True: meant to run beside other provers on the same
+        GPU (batched-affine pair rounds in the bucket accumulation: more proofs/s, slightly slower alone)."""
         self.zkey = zkey
         h = C.c_void_p()
-        check(_lib.load().nzcp_prover_create(zkey._h, C.byref(h)))
+        check(_lib.load().nzcp_prover_create_mode(zkey._h, 1 if throughput else 0, C.byref(h)))
         self._h = h
 
     def _finish(self, proof, dbg, want_h, hbuf):
@@ -184,10 +186,10 @@ class ProverPool:
     reduction trees, host finalisation) overlaps the integer-pipe-bound kernels of the next.  ctypes drops the GIL inside
     the library calls.  Proof i is independent of proof j: this is the batch mode of SURVEY.md 8e on ONE GPU."""
 
-    def __init__(self, zkey, n_provers=2):
+    def __init__(self, zkey, n_provers=2, throughput=True):
         from concurrent.futures import ThreadPoolExecutor
         self.zkey = zkey
-        self.provers = [Prover(zkey) for _ in range(max(1, int(n_provers)))]
+        self.provers = [Prover(zkey, throughput=throughput) for _ in range(max(1, int(n_provers)))]
         self._pool = ThreadPoolExecutor(max_workers=len(self.provers))
 
     def _run(self, method, items, r, s, kw):

@@ -130,6 +130,7 @@ struct MsmSort {
   size_t round_max[kMsmMaxRounds + 1] = {0, 0, 0, 0};   // upper bound of the point count after round r
 };
 int msm_pick_rounds(size_t n_points, int c);
+int msm_pick_rounds_throughput(size_t n_points, int c);
 void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds = -1, bool table_free = false);   // rounds < 0: msm_pick_rounds
 void msm_sort_destroy(MsmSort* s);
 void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_t st);

@@ -819,7 +819,8 @@ std::atomic<int> g_tune_rounds{-1};
 std::atomic<int> g_tune_rounds_w{-1}, g_tune_rounds_h{-1};   // prover: witness MSMs / H MSM (-1 = default)
 std::atomic<int> g_tune_pair_k[kMsmMaxRounds] = {{16}, {16}, {16}};
 
-// Pair rounds are OFF unless asked for (nzcp_tuning_set "msm_rounds" / "prover_rounds_*").  Measured on the B200
+// Pair rounds are OFF for a prover in latency mode and for the standalone MSMs unless asked for (nzcp_tuning_set
+// "msm_rounds" / "prover_rounds_*"); throughput-mode provers turn them on (msm_pick_rounds_throughput).  Measured on the B200
 // (profiles/r02_pair_rounds.md): they cut the executed products of the H accumulation by a third, but an affine
 // addition needs each operand twice (denominator pass, then the addition itself) and round 1 gathers its operands
 // from the 1 GB window table -- random 128-byte lines come in at ~3.7 TB/s, so round 1 alone costs what the XYZZ kernel
@@ -831,6 +832,14 @@ int msm_pick_rounds(size_t n_points, int c) {
   const int forced = g_tune_rounds.load();
   if (forced >= 0) return forced > kMsmMaxRounds ? kMsmMaxRounds : forced;
   return 0;
+}
+
+// Throughput mode (several proofs in flight per GPU): three pair rounds once an MSM has a few million entries -- below
+// that the rounds' nine extra launches cost more than the products they save.
+int msm_pick_rounds_throughput(size_t n_points, int c) {
+  const int forced = g_tune_rounds.load();
+  if (forced >= 0) return forced > kMsmMaxRounds ? kMsmMaxRounds : forced;
+  return n_points * (size_t)msm_num_windows(c) >= ((size_t)1 << 22) ? kMsmMaxRounds : 0;
 }
 
 template <class T>

@@ -271,7 +271,10 @@ static void prover_release(nzcp_prover* p) {
   delete p;
 }
 
-static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
+// mode 0 = latency (a lone proof at a time: XYZZ bucket accumulation only), mode 1 = throughput (several provers in flight:
+// the batched-affine pair rounds of msm_pair.cuh on every MSM -- their gather-bound passes overlap the multiplier-bound
+// kernels of the other proofs; measured +5 % proofs/s at +0.45 ms lone-proof latency, profiles/r02_window_rounds_sweep.md).
+static nzcp_prover* prover_create_impl(nzcp_zkey* zk, int mode = 0) {
   use_device(zk->device);
   std::unique_ptr<nzcp_prover, void (*)(nzcp_prover*)> p(new nzcp_prover(), prover_release);
   p->zk = zk;
@@ -286,10 +289,9 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk) {
   NZCP_CUDA(cudaMalloc(&p->d_wtns, (size_t)zk->n_vars * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_abc, 3 * n * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_h, n * sizeof(Fr)));
-  // Batched-affine pair rounds (msm_pair.cuh) are an opt-in: see msm_pick_rounds for the measurement behind the default.
   int rounds_h = g_tune_rounds_h.load(), rounds_w = g_tune_rounds_w.load();
-  if (rounds_h < 0) rounds_h = msm_pick_rounds(n, zk->c_h);
-  if (rounds_w < 0) rounds_w = msm_pick_rounds(zk->n_vars, zk->c_w);
+  if (rounds_h < 0) rounds_h = mode == 1 ? msm_pick_rounds_throughput(n, zk->c_h) : msm_pick_rounds(n, zk->c_h);
+  if (rounds_w < 0) rounds_w = mode == 1 ? msm_pick_rounds_throughput(zk->n_vars, zk->c_w) : msm_pick_rounds(zk->n_vars, zk->c_w);
   msm_sort_create(&p->sort_w, zk->n_vars, zk->c_w, rounds_w);
   msm_sort_create(&p->sort_h, n, zk->c_h, rounds_h);
   msm_run_create(&p->run_a, &p->sort_w, false);
@@ -566,6 +568,15 @@ int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out) {
   });
 }
 
+int nzcp_prover_create_mode(nzcp_zkey* zk, int mode, nzcp_prover** out) {
+  return api_guard([&] {
+    if (!zk || !out) throw ApiError(NZCP_E_ARG, "null argument");
+    if (mode != 0 && mode != 1) throw ApiError(NZCP_E_ARG, "prover mode must be 0 (latency) or 1 (throughput)");
+    *out = nullptr;
+    *out = prover_create_impl(zk, mode);
+  });
+}
+
 void nzcp_prover_free(nzcp_prover* p) { prover_release(p); }
 
 int nzcp_prove(nzcp_prover* p, const uint8_t* wtns, size_t wtns_len, const uint8_t* r, const uint8_t* s,
@@ -628,7 +639,7 @@ int nzcp_prove_batch(nzcp_zkey* zk, const uint8_t* const* wtns, const size_t* wt
       nzcp_zkey* zk; std::vector<nzcp_prover*>* v;
       ~Return() { std::lock_guard<std::mutex> lk(zk->pool_mu); for (auto* p : *v) zk->pool.push_back(p); }
     } ret{zk, &mine};
-    while ((int)mine.size() < n_provers) mine.push_back(prover_create_impl(zk));
+    while ((int)mine.size() < n_provers) mine.push_back(prover_create_impl(zk, 1));   // throughput mode
     std::vector<int> codes(n_proofs, NZCP_OK);
     std::vector<std::string> msgs(n_provers);
     std::vector<std::thread> threads;

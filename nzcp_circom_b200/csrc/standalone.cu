@@ -11,9 +11,6 @@ namespace nzcp {
 extern std::atomic<int> g_tune_rounds;                   // msm.cu
 extern std::atomic<int> g_tune_pair_k[kMsmMaxRounds];
 extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;
-extern std::atomic<int> g_tune_ntt_tma;   // ntt.cu
-extern std::atomic<int> g_tune_c_h, g_tune_c_w;   // prover.cu
-extern std::atomic<int> g_tune_stage_mode, g_tune_stage_chunk_kb, g_tune_stage_threads;   // prover.cu
 
 G1Affine g1_generator();  // synth.cu
 Fr host_fr_root(int k);     // ntt.cu
@@ -700,26 +697,6 @@ int nzcp_host_msm_sim(const uint8_t* bases, const uint8_t* scalars, size_t n_poi
     if (window_bits < 2 || window_bits > 16 || rounds < 0 || rounds > kMsmMaxRounds) throw ApiError(NZCP_E_ARG, "bad window / rounds");
     if (g2) g2_to_plain_bytes(host_msm_sim<Fq2>(bases, scalars, n_points, window_bits, rounds, adds_per_thread), out);
     else g1_to_plain_bytes(host_msm_sim<Fq>(bases, scalars, n_points, window_bits, rounds, adds_per_thread), out);
-  });
-}
-
-int nzcp_tuning_set(const char* name, int value) {
-  return api_guard([&] {
-    if (!name) throw ApiError(NZCP_E_ARG, "null argument");
-    const std::string k(name);
-    if (k == "msm_rounds") g_tune_rounds.store(value);
-    else if (k == "prover_rounds_w") g_tune_rounds_w.store(value);
-    else if (k == "prover_rounds_h") g_tune_rounds_h.store(value);
-    else if (k == "pair_k1") g_tune_pair_k[0].store(value);
-    else if (k == "pair_k2") g_tune_pair_k[1].store(value);
-    else if (k == "pair_k3") g_tune_pair_k[2].store(value);
-    else if (k == "stage_mode") g_tune_stage_mode.store(value);
-    else if (k == "stage_chunk_kb") g_tune_stage_chunk_kb.store(value);
-    else if (k == "stage_threads") g_tune_stage_threads.store(value);
-    else if (k == "ntt_tma") g_tune_ntt_tma.store(value);
-    else if (k == "prover_c_h") g_tune_c_h.store(value);
-    else if (k == "prover_c_w") g_tune_c_w.store(value);
-    else throw ApiError(NZCP_E_ARG, "unknown tuning knob: " + k);
   });
 }
 

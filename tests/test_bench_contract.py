@@ -1,5 +1,7 @@
-"""CPU: the committed bench lines (profiles/r01_bench_*.json, produced by bench.py on B200s) carry every key the
-measurement contract asks for, and the numbers in them are self-consistent (value = proofs / time, frac = achieved / peak)."""
+"""CPU: the committed bench lines (profiles/r0N_bench_*.json, produced by bench.py on B200s) carry every key the
+measurement contract asks for, and the numbers in them are self-consistent (value = proofs / time, frac = achieved / peak).
+Round-2 lines additionally: identical `config` on both arms, the pageable-memory e2e figure, the whole-step roofline,
+the pairing check of a timed proof, and the extras (BASELINE configs[2] and configs[4])."""
 import glob
 import json
 import os
@@ -7,7 +9,8 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_*.json")))
+LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[12]_bench_*.json")))
+R02 = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_*.json")))
 
 
 @pytest.mark.parametrize("path", LINES, ids=[os.path.basename(p) for p in LINES])
@@ -46,3 +49,37 @@ def test_reference_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] and d["cpu_baseline"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+@pytest.mark.parametrize("path", R02, ids=[os.path.basename(p) for p in R02])
+def test_round2_line_additions(path):
+    d = json.load(open(path))
+    assert d["proof_verifies"] is True
+    pg = d["e2e"]["pageable"]
+    assert 0 < pg["value"] <= d["value"] * 1.02 and 0 < pg["value_driver_staged"] <= d["value"] * 1.02
+    assert d["p50_latency_ms_pageable"] >= d["p50_latency_ms"] * 0.9
+    rs = d["roofline_step"]
+    tot = rs["canonical_fq_mul_per_proof"]
+    assert tot["total"] == tot["bucket_additions"] + tot["per_window_bucket_reduction"] + tot["ntt"] + tot["r1cs_and_join"]
+    per_gpu = d["value"] / d["n_gpus"]
+    assert rs["achieved"] == pytest.approx(tot["total"] * per_gpu / 1e9, rel=1e-9)
+    assert rs["frac"] == pytest.approx(rs["achieved"] / rs["peak"], rel=1e-9) and 0.5 < rs["frac_without_reduction_term"] < 1
+    assert "traffic_source" in d["roofline"] and "modes" in d
+    if "extras" in d:
+        ex = d["extras"]
+        c2, c4 = ex["config2_batch"], ex["config4_split_msm"]
+        assert c2["proofs"] == 1024 and c2["scaling"] == "strong" and c2["n_gpus"] == d["n_gpus"]
+        assert c2["proofs_per_s"] == pytest.approx(c2["proofs"] / c2["seconds"], rel=1e-9)
+        assert c4["n_gpus"] == d["n_gpus"] and c4["points_per_gpu"] * d["n_gpus"] >= 1 << 24
+        assert 0 < c4["kernel_ms_max_over_ranks"] <= c4["ms"]
+
+
+def test_round2_reference_arm_has_the_same_config():
+    ref = os.path.join(ROOT, "profiles", "r02_ref_n1.json")
+    main = os.path.join(ROOT, "profiles", "r02_bench_default.json")
+    if not (os.path.exists(ref) and os.path.exists(main)):
+        pytest.skip("round-2 records not committed yet")
+    r, m = json.load(open(ref)), json.load(open(main))
+    assert r["config"] == m["config"]
+    assert r["impl"] == "reference" and r["metric"] == m["metric"] and r["unit"] == m["unit"]
+    assert r["cpu_baseline"]["kind"] == "port" and r["e2e"]["value"] == r["value"]

@@ -47,6 +47,11 @@ def test_benchmarked_shape_h_msms_proof_bit_exact(lib, shape):
             if seed == 1:
                 first = got["proof"]
         assert got["proof"] != first
+        # throughput-mode prover (three batched-affine pair rounds on every MSM at this size): the same five MSM results
+        with api.Prover(zk, throughput=True) as pt:
+            got_t = pt.prove(wb, r=R_FIXED, s=S_FIXED, debug=True)
+            for k in ("msm_a", "msm_b1", "msm_b2", "msm_c", "msm_h", "proof"):
+                assert got_t[k] == exp[k], "throughput mode: " + k
         # the same witness through the batch entry point (several provers in flight) gives the same bytes
         assert zk.prove_batch([wb, wb, wb], [R_FIXED] * 3, [S_FIXED] * 3, n_provers=3) == [got["proof"]] * 3
     # and it is a valid Groth16 proof (independent pairing check)
