@@ -62,7 +62,7 @@ static void parse_container(const uint8_t* b, size_t len, const char magic[4], u
     uint64_t sl = rd64(b + pos + 4);
     pos += 12;
     if (sl > len - pos) throw ApiError(NZCP_E_FORMAT, "section exceeds file size");
-    if ((int)id <= max_id && secs[id].p == nullptr) {
+    if (id <= (uint32_t)max_id && secs[id].p == nullptr) {   // unsigned compare: a section id >= 2^31 must not index backwards
       secs[id].p = b + pos;
       secs[id].len = sl;
     }

@@ -53,7 +53,7 @@ void parse_bin(const uint8_t* b, size_t len, const char* magic, Sect* secs, int 
     const uint64_t sl = rd64u(b + pos + 4);
     pos += 12;
     if (sl > len - pos) throw ApiError(NZCP_E_FORMAT, "section exceeds file size");
-    if ((int)id <= max_id && !secs[id].p) { secs[id].p = b + pos; secs[id].len = sl; }
+    if (id <= (uint32_t)max_id && !secs[id].p) { secs[id].p = b + pos; secs[id].len = sl; }
     pos += sl;
   }
 }
