@@ -64,7 +64,7 @@ def test_round2_line_additions(path):
     per_gpu = d["value"] / d["n_gpus"]
     assert rs["achieved"] == pytest.approx(tot["total"] * per_gpu / 1e9, rel=1e-9)
     assert rs["frac"] == pytest.approx(rs["achieved"] / rs["peak"], rel=1e-9) and 0.5 < rs["frac_without_reduction_term"] < 1
-    assert "traffic_source" in d["roofline"] and "modes" in d
+    assert "traffic_source" in d["roofline"] and ("modes" in d or "modes" in d["config"])
     if "extras" in d:
         ex = d["extras"]
         c2, c4 = ex["config2_batch"], ex["config4_split_msm"]
@@ -80,6 +80,6 @@ def test_round2_reference_arm_has_the_same_config():
     if not (os.path.exists(ref) and os.path.exists(main)):
         pytest.skip("round-2 records not committed yet")
     r, m = json.load(open(ref)), json.load(open(main))
-    assert r["config"] == m["config"]
+    assert r["config"] == {k: v for k, v in m["config"].items() if k != "modes"}
     assert r["impl"] == "reference" and r["metric"] == m["metric"] and r["unit"] == m["unit"]
     assert r["cpu_baseline"]["kind"] == "port" and r["e2e"]["value"] == r["value"]
