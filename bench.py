@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--provers", type=int, default=4, help="concurrent provers (host threads + stream sets) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-runs", type=int, default=50, help="lone proofs timed for p50_latency_ms")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2] / configs[4] records")
     ap.add_argument("--extras-proofs", type=int, default=1024, help="configs[2]: proofs in the sharded batch")
     ap.add_argument("--extras-msm-log", type=int, default=24, help="configs[4]: log2 points of the split G1 MSM")
@@ -322,14 +323,16 @@ def main():
     step_e2e_pageable()
     ms_e2e_pg_direct = timed(step_e2e_pageable, args.steps)
     api.tuning_set("stage_mode", -1)
-    latency_run(max(8, B))
+    latency_run(5)                      # warm the latency-mode prover (its own work buffers, first-touch of the staging path)
+    del lat[:]
+    latency_run(args.latency_runs)      # BASELINE configs[1]: one proof at a time, p50 over the runs
     lat_pinned = list(lat)
     del lat[:]
-    for i in range(max(8, B)):          # lone-proof latency from pageable memory
+    for i in range(5 + args.latency_runs):          # lone-proof latency from pageable memory (first 5 = warm-up)
         t = time.perf_counter()
         pr.prove(pageable[i % B], r=R_FIXED, s=S_FIXED)
         lat.append(time.perf_counter() - t)
-    lat_pageable, lat[:] = list(lat), lat_pinned
+    lat_pageable, lat[:] = list(lat[5:]), lat_pinned
 
     # per-stage device times + the dominant kernel, from the library's own CUDA events (one extra proof, not timed above)
     dbg = pr.prove_device(d_wit[0], r=R_FIXED, s=S_FIXED, debug=True)
@@ -357,6 +360,8 @@ def main():
                                          "= through the prover's pinned staging buffer in 1 MiB chunks (default), "
                                          "`value_driver_staged` = cudaMemcpyAsync straight from the pageable buffer"}},
             "p50_latency_ms": 1e3 * statistics.median(lat) if lat else None,
+            "latency_ms": {"runs": len(lat), "p50": 1e3 * statistics.median(lat), "min": 1e3 * min(lat), "max": 1e3 * max(lat),
+                           "p90": 1e3 * sorted(lat)[int(0.9 * (len(lat) - 1))]} if lat else None,
             "p50_latency_ms_pageable": 1e3 * statistics.median(lat_pageable) if lat_pageable else None,
             "gpu_launches": launches, "clocks": clocks, "stage_ms": dbg["stage_ms"],
         }
@@ -366,7 +371,7 @@ def main():
         line["roofline_step"] = step_roofline(dbg, zk, value / world, line["roofline"]["peak"] if "roofline" in line else None)
         line["modes"] = ("value / e2e: %d throughput-mode provers in flight (batched-affine pair rounds on); "
                                    "p50_latency_ms, stage_ms, roofline: one latency-mode prover, lone proofs" % args.provers)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # the CPU leg runs at N = 1 only (rank 0's cores are shared at N > 1)
             times, stages, thr, cproof = cpu_reference_proofs(zkey, wtns, 1)
             correct = (cproof == dbg["proof"])
             line["cpu_baseline"] = {"value": 1.0 / times[0], "unit": "proofs/s", "cores": thr, "kind": "port",

@@ -626,6 +626,7 @@ int nzcp_prove_batch(nzcp_zkey* zk, const uint8_t* const* wtns, const size_t* wt
   return api_guard([&] {
     if (!zk || (n_proofs && (!wtns || !wtns_len || !proofs))) throw ApiError(NZCP_E_ARG, "null argument");
     if (n_provers < 1) n_provers = 3;
+    if (n_provers > 16) n_provers = 16;   // a throughput-mode prover holds ~6 GB of scratch at the NZCP size
     if ((size_t)n_provers > n_proofs) n_provers = (int)(n_proofs ? n_proofs : 1);
     std::vector<nzcp_prover*> mine;
     {

@@ -165,18 +165,67 @@ def prove(zkeyFileName, witnessFileName, logger=None, *, r=None, s=None, device=
     return {"proof": proof_from_bytes(res["proof"]), "publicSignals": _public_signals(wt, zk.n_public)}
 
 
-def fullProve(input, wasmFile, zkeyFileName, logger=None, *, r=None, s=None, device=0):
+_NODE_WTNS_SCRIPT = (
+    'const snarkjs = require("snarkjs"); const fs = require("fs");'
+    '(async () => { const input = JSON.parse(fs.readFileSync(process.argv[1], "utf8"));'
+    ' await snarkjs.wtns.calculate(input, process.argv[2], process.argv[3]); process.exit(0); })()'
+    '.catch((e) => { console.error(e && e.message ? e.message : String(e)); process.exit(1); });')
+
+
+def calculate_witness(input, wasmFile, node=None, cwd=None):
+    """snarkjs `wtns.calculate(input, wasmFile, wtns)` -- the step BEFORE the proving path: it runs the
+    circom-generated WASM on the CPU and is out of scope for the GPU work, so it is delegated to the reference's own
+    toolchain: a `node` process with snarkjs installed (circom_runtime's WitnessCalculator underneath).  `node`: the
+    executable (default: $NZCP_NODE or "node" on PATH); `cwd`: where `require("snarkjs")` resolves (the reference
+    checkout with its node_modules).  Returns the .wtns image.  Raises NzcpError(NZCP_E_ARG) when no node is available --
+    there is no WASM runtime inside this package."""
+    import json
+    import shutil
+    import subprocess
+    import tempfile
+    exe = node or os.environ.get("NZCP_NODE") or shutil.which("node")
+    if not exe or (os.path.sep in exe and not os.path.exists(exe)):
+        raise NzcpError(_lib.NZCP_E_ARG,
+                        "fullProve: witness calculation needs node + snarkjs (the reference's own toolchain) and no node "
+                        "executable was found; pass a witness-calculator callable as wasmFile, or call prove() with a .wtns")
+    wasm = os.fspath(wasmFile)
+    if not os.path.exists(wasm):
+        raise NzcpError(_lib.NZCP_E_ARG, "fullProve: wasm file not found: %s" % wasm)
+    with tempfile.TemporaryDirectory(prefix="nzcp_wtns_") as d:
+        inp, out = os.path.join(d, "input.json"), os.path.join(d, "witness.wtns")
+        def js_safe(v):   # integers beyond 2^53 travel as decimal strings (JSON.parse would round them; snarkjs accepts strings)
+            if isinstance(v, bool) or v is None or isinstance(v, str):
+                return v
+            if isinstance(v, int):
+                return v if -(1 << 53) < v < (1 << 53) else str(v)
+            if isinstance(v, dict):
+                return {str(k): js_safe(x) for k, x in v.items()}
+            if isinstance(v, (list, tuple)):
+                return [js_safe(x) for x in v]
+            return str(v)
+        with open(inp, "w") as f:
+            json.dump(js_safe(input), f)
+        res = subprocess.run([exe, "-e", _NODE_WTNS_SCRIPT, inp, os.path.abspath(wasm), out], cwd=cwd, capture_output=True, text=True)
+        if res.returncode != 0 or not os.path.exists(out):
+            raise NzcpError(_lib.NZCP_E_ARG, "fullProve: witness calculation failed: %s" % (res.stderr.strip() or res.stdout.strip()))
+        with open(out, "rb") as f:
+            return f.read()
+
+
+def fullProve(input, wasmFile, zkeyFileName, logger=None, *, r=None, s=None, device=0, node=None, node_cwd=None):
     """groth16.fullProve: witness calculation (circom-generated WASM, CPU) followed by prove().
 
-    The witness generator is outside the hot path and no WASM runtime ships with this package:
-    `wasmFile` must be a callable `calc(input) -> .wtns bytes` (e.g. a binding of circom_runtime's
-    WitnessCalculator); the Node module in js/ passes snarkjs's own `wtns.calculate` here.  A path to a .wasm raises.
+    The witness generator is outside the hot path.  `wasmFile` may be
+      * a callable `calc(input) -> .wtns bytes` (any binding of circom_runtime's WitnessCalculator), or
+      * a path to the circuit's .wasm, as in snarkjs: the witness is then computed by the reference's own toolchain in a
+        `node` child process (calculate_witness above); without node this raises -- no WASM runtime ships here.
     """
-    if not callable(wasmFile):
-        raise NzcpError(_lib.NZCP_E_ARG,
-                        "fullProve: no WASM runtime in this build; pass a witness calculator callable as wasmFile "
-                        "(the Node module js/index.js uses circom_runtime for this step)")
-    wtns = wasmFile(input)
+    if callable(wasmFile):
+        wtns = wasmFile(input)
+    else:
+        if logger:
+            logger.debug("Calculating the witness with node + snarkjs")
+        wtns = calculate_witness(input, wasmFile, node=node, cwd=node_cwd)
     return prove(zkeyFileName, {"type": "mem", "data": wtns}, logger, r=r, s=s, device=device)
 
 

@@ -1,7 +1,7 @@
 """Whole-proof multiplier-pipe time from an ncu launch list that carries, per launch, gpu__time_duration.sum and
 sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed: sum(duration x fmaheavy%) over the launches of ONE
 proof = the time the IMAD.WIDE pipe is busy per proof; divided by the measured ms/proof of the un-profiled bench it is
-the whole-step pipe utilisation.  Usage: pipe_summary.py launches_pipe.csv [ms_per_proof]"""
+the whole-step pipe utilisation.  Usage: pipe_summary.py launches_pipe.csv [ms_per_proof [kernel-name-substring the proof must contain]]"""
 import collections
 import csv
 import re
@@ -9,6 +9,7 @@ import sys
 
 path = sys.argv[1]
 ms_per_proof = float(sys.argv[2]) if len(sys.argv) > 2 else None
+must_contain = sys.argv[3] if len(sys.argv) > 3 else None     # e.g. "msm_pair": pick a throughput-mode proof
 with open(path) as f:
     rows = list(csv.DictReader([l for l in f if not l.startswith("==")]))
 launch = collections.OrderedDict()
@@ -20,6 +21,11 @@ ls = list(launch.values())
 starts = [i for i, l in enumerate(ls) if "r1cs_eval" in l["name"]]
 # one proof = the launches from one r1cs evaluation up to the next (the last complete interval of the capture)
 proof = ls[starts[-2]:starts[-1]]
+if must_contain:
+    for a, b in reversed(list(zip(starts, starts[1:]))):
+        if any(must_contain in l["name"] for l in ls[a:b]):
+            proof = ls[a:b]
+            break
 agg = collections.OrderedDict()
 for l in proof:
     t = l["gpu__time_duration.sum"] / 1e3
