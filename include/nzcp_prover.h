@@ -133,9 +133,10 @@ int nzcp_zkey_new(const uint8_t* r1cs, size_t r1cs_len, const uint8_t* ptau, siz
 
 /* Work buffers + streams for proofs against `zk`.  Several provers may share one zkey (one per host thread). */
 int nzcp_prover_create(nzcp_zkey* zk, nzcp_prover** out);   /* = mode 0 */
-/* mode 0 = latency (one proof at a time, lowest per-proof latency), mode 1 = throughput (meant to run beside other provers
- * on the same GPU: bucket accumulation goes through batched-affine pair rounds, +5 % proofs/s, +0.45 ms per lone proof,
- * ~6 GB more scratch).  nzcp_prove_batch uses throughput-mode provers.  Same proofs, bit for bit, in both modes. */
+/* mode 0 = latency (one proof at a time), mode 1 = throughput (meant to run beside other provers on the same GPU;
+ * nzcp_prove_batch uses these).  Same proofs, bit for bit, in both modes; today both run the same kernels (batched-affine
+ * pair rounds on every large MSM, ~6 GB of scratch per prover at the NZCP size) -- the distinction is kept in the ABI so
+ * that a caller states its use. */
 int nzcp_prover_create_mode(nzcp_zkey* zk, int mode, nzcp_prover** out);
 void nzcp_prover_free(nzcp_prover* p);
 
@@ -198,6 +199,10 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
  *   "msm_rounds"  batched-affine pair rounds per MSM: -1 = automatic (by size), 0..3 forced
  *   "prover_rounds_w" / "prover_rounds_h"  the same for a prover's witness MSMs / H MSM (read by nzcp_prover_create)
  *   "pair_k1" / "pair_k2" / "pair_k3"  additions per thread in round 1 / 2 / 3: 4, 8, 16 or 32
+ *   "pair_prefetch_fwd" / "pair_prefetch_bwd"  operand prefetch in the pair-round kernels: 0 = none (default), 1 = L1, 2 = L2
+ *   "pair_stage"  1 = round 1's forward pass stages the operands it gathered and the backward pass streams them (set it before
+ *                 the prover / plan is created); 0 (default) = the backward pass gathers them from the window table again
+ *   "acc_prefetch"  1 (default) = the XYZZ accumulate kernel prefetches its next table point to L1, 0 = no prefetch
  *   "stage_mode"  host witness upload in nzcp_prove*: -1 = automatic (pageable memory through the prover's pinned staging
  *                 buffer in chunks, caller-pinned memory directly), 0 = always direct, 1 = always staged
  *   "stage_chunk_kb"  staging chunk size in KiB (default 1024)

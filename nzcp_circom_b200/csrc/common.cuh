@@ -130,7 +130,7 @@ struct MsmSort {
   size_t round_max[kMsmMaxRounds + 1] = {0, 0, 0, 0};   // upper bound of the point count after round r
 };
 int msm_pick_rounds(size_t n_points, int c);
-int msm_pick_rounds_throughput(size_t n_points, int c);
+int msm_pick_rounds_prover(size_t n_points, int c);
 void msm_sort_create(MsmSort* s, size_t n_points, int c, int rounds = -1, bool table_free = false);   // rounds < 0: msm_pick_rounds
 void msm_sort_destroy(MsmSort* s);
 void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_t st);
@@ -156,6 +156,7 @@ struct MsmRun {
   cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;  // around the bucket accumulation (pair rounds + XYZZ kernel)
   void* round_pts[2] = {nullptr, nullptr};   // affine point arrays of the pair rounds (ping-pong)
   void* round_prefix = nullptr;              // prefix products of the shared inversion, [step][thread]
+  void* round_ops = nullptr;                 // round 1: the two operands of every addition, staged by the forward pass
   void* round_prod = nullptr;                // per-thread denominator products, inverted in place between the passes
   size_t scratch_bytes = 0;
 };

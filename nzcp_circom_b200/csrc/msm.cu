@@ -449,18 +449,18 @@ template <> struct AccumOcc<Fq2> { static constexpr int kBlocks = NZCP_G2_ACC_BL
 template <class F>
 __global__ void __launch_bounds__(128, AccumOcc<F>::kBlocks)
 msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,
-                      const uint2* __restrict__ tasks, const uint32_t* __restrict__ flags, XYZZ<F>* __restrict__ partial) {
+                      const uint2* __restrict__ tasks, const uint32_t* __restrict__ flags, XYZZ<F>* __restrict__ partial, int pf) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= flags[2]) return;
   uint2 tk = tasks[t];
   XYZZ<F> acc = XYZZ<F>::inf();
   uint32_t e = entries[tk.x];
-  prefetch_l1(table + (e & 0x7fffffffu));
+  if (pf) prefetch_l1(table + (e & 0x7fffffffu));
   for (uint32_t k = 0; k < tk.y; k++) {
     uint32_t en = e;
     if (k + 1 < tk.y) {
       en = entries[tk.x + k + 1];
-      prefetch_l1(table + (en & 0x7fffffffu));
+      if (pf) prefetch_l1(table + (en & 0x7fffffffu));
     }
     Affine<F> q = table[e & 0x7fffffffu];
     if (!q.is_inf()) xyzz_madd(acc, q, (e >> 31) != 0);
@@ -488,14 +488,17 @@ msm_accumulate_pts_kernel(const Affine<F>* __restrict__ pts, const uint2* __rest
 // One pair round (msm_pair.cuh) = forward, invert, backward; thread t of forward / backward owns K consecutive points of
 // the round, thread g of invert owns 32 consecutive thread products.
 static constexpr int kPairInvGroup = 32;
+#ifndef NZCP_PAIR_FWD_BLOCKS
+#define NZCP_PAIR_FWD_BLOCKS 1
+#endif
 template <class F, bool FROM_TABLE, int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? NZCP_PAIR_FWD_BLOCKS : 1))
 msm_pair_forward_kernel(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
                         const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t n_buckets,
-                        F* __restrict__ scratch, F* __restrict__ prod) {
+                        F* __restrict__ scratch, F* __restrict__ prod, int pf, Affine<F>* __restrict__ ops) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  PairSource<F, FROM_TABLE> ps{src, entries};
-  msm_pair_forward_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, scratch, prod);
+  PairSource<F, FROM_TABLE> ps{src, entries, pf};
+  msm_pair_forward_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, scratch, prod, ops);
 }
 
 template <class F, int K>
@@ -510,10 +513,12 @@ template <class F, bool FROM_TABLE, int K>
 __global__ void __launch_bounds__(128)
 msm_pair_backward_kernel(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
                          const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t n_buckets,
-                         Affine<F>* __restrict__ dst, const F* __restrict__ scratch, const F* __restrict__ inv_prod) {
+                         Affine<F>* __restrict__ dst, const F* __restrict__ scratch, const F* __restrict__ inv_prod, int pf,
+                         const Affine<F>* __restrict__ ops) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  PairSource<F, FROM_TABLE> ps{src, entries};
-  msm_pair_backward_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, dst, scratch, inv_prod);
+  PairSource<F, FROM_TABLE> ps{src, entries, pf};
+  msm_pair_backward_body<F, FROM_TABLE, K>(t, gridDim.x * blockDim.x, ps, off_in, off_out, n_buckets, dst, scratch, inv_prod,
+                                           ops);
 }
 
 // L2-coherent load of an object another block of the same grid wrote (after its __threadfence + counter increment).
@@ -818,9 +823,16 @@ int msm_num_windows(int c) {
 std::atomic<int> g_tune_rounds{-1};
 std::atomic<int> g_tune_rounds_w{-1}, g_tune_rounds_h{-1};   // prover: witness MSMs / H MSM (-1 = default)
 std::atomic<int> g_tune_pair_k[kMsmMaxRounds] = {{16}, {16}, {16}};
+std::atomic<int> g_tune_pair_prefetch[2] = {{0}, {0}};   // forward / backward pair kernels: 0 none, 1 L1, 2 L2 (msm_pair.cuh)
+// "pair_stage" = 1: round 1's forward pass also writes the operands it gathered (coalesced) and the backward pass streams
+// them instead of gathering a second time.  Measured on the B200: it LOSES 4 % (126 vs 131 proofs/s,
+// profiles/r02_window_rounds_sweep.md) -- the 2 x 1 GB of extra streaming per H MSM and a forward pass that now carries
+// whole points through its registers cost more than the second gather saves.  Kept as an opt-in, off by default.
+std::atomic<int> g_tune_pair_stage{0};
+std::atomic<int> g_tune_acc_prefetch{1};                 // XYZZ accumulate kernel: prefetch the next table point to L1
 
-// Pair rounds are OFF for a prover in latency mode and for the standalone MSMs unless asked for (nzcp_tuning_set
-// "msm_rounds" / "prover_rounds_*"); throughput-mode provers turn them on (msm_pick_rounds_throughput).  Measured on the B200
+// Pair rounds are OFF for the standalone MSMs unless asked for (nzcp_tuning_set "msm_rounds"); provers turn them on
+// (msm_pick_rounds_prover; "prover_rounds_*" override).  First measurement on the B200, H MSM alone, operand prefetch ON
 // (profiles/r02_pair_rounds.md): they cut the executed products of the H accumulation by a third, but an affine
 // addition needs each operand twice (denominator pass, then the addition itself) and round 1 gathers its operands
 // from the 1 GB window table -- random 128-byte lines come in at ~3.7 TB/s, so round 1 alone costs what the XYZZ kernel
@@ -834,9 +846,9 @@ int msm_pick_rounds(size_t n_points, int c) {
   return 0;
 }
 
-// Throughput mode (several proofs in flight per GPU): three pair rounds once an MSM has a few million entries -- below
-// that the rounds' nine extra launches cost more than the products they save.
-int msm_pick_rounds_throughput(size_t n_points, int c) {
+// The prover's MSMs: three pair rounds once an MSM has a few million entries -- below that the rounds' nine extra launches
+// cost more than the products they save.
+int msm_pick_rounds_prover(size_t n_points, int c) {
   const int forced = g_tune_rounds.load();
   if (forced >= 0) return forced > kMsmMaxRounds ? kMsmMaxRounds : forced;
   return n_points * (size_t)msm_num_windows(c) >= ((size_t)1 << 22) ? kMsmMaxRounds : 0;
@@ -1046,6 +1058,8 @@ void msm_run_create(MsmRun* r, const MsmSort* sort, bool g2) {
     r->round_pts[0] = dev_alloc<unsigned char>((sort->round_max[1] + pad) * asz, &tot);
     if (sort->rounds > 1) r->round_pts[1] = dev_alloc<unsigned char>((sort->round_max[2] + pad) * asz, &tot);
     r->round_prefix = dev_alloc<unsigned char>((sort->round_max[1] + pad) * fsz, &tot);
+    if (g_tune_pair_stage.load())   // opt-in ("pair_stage", read when the run is created): two operands per round-1 addition
+      r->round_ops = dev_alloc<unsigned char>((sort->round_max[1] + pad) * 2 * asz, &tot);
     r->round_prod = dev_alloc<unsigned char>((sort->round_max[1] / 4 + pad) * fsz, &tot);   // >= 4 additions per thread
   }
   NZCP_CUDA(cudaEventCreate(&r->ev_acc0));
@@ -1067,6 +1081,7 @@ void msm_run_destroy(MsmRun* r) {
   cudaFree(r->round_pts[0]);
   cudaFree(r->round_pts[1]);
   cudaFree(r->round_prefix);
+  cudaFree(r->round_ops);
   cudaFree(r->round_prod);
   if (r->out_host) cudaFreeHost(r->out_host);
   if (r->ev_acc0) cudaEventDestroy(r->ev_acc0);
@@ -1087,7 +1102,8 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
   NZCP_CUDA(cudaEventRecord(r->ev_acc0, st));
   if (s->rounds == 0) {
     msm_accumulate_kernel<F><<<div_up(s->max_tasks, 128), 128, 0, st>>>(reinterpret_cast<const Affine<F>*>(t->pts),
-                                                                       s->entries, s->tasks, s->flags, partial);
+                                                                       s->entries, s->tasks, s->flags, partial,
+                                                                       g_tune_acc_prefetch.load());
     NZCP_LAUNCH_CHECK();
   } else {
     // pair rounds: table -> pts[0] -> pts[1] -> pts[0]; then the XYZZ accumulation over the last array
@@ -1096,20 +1112,24 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
       Affine<F>* dst = reinterpret_cast<Affine<F>*>(r->round_pts[(rd - 1) & 1]);
       const uint32_t* off_in = s->round_off + (size_t)(rd - 1) * (nb + 1);
       const uint32_t* off_out = s->round_off + (size_t)rd * (nb + 1);
+      const int pf_fwd = g_tune_pair_prefetch[0].load(), pf_bwd = g_tune_pair_prefetch[1].load();
       int k = g_tune_pair_k[rd - 1].load();
       k = k >= 32 ? 32 : k >= 16 ? 16 : k >= 8 ? 8 : 4;
       const unsigned grid = div_up(div_up(s->round_max[rd], k), 128);
       const unsigned grid_inv = div_up(div_up((size_t)grid * 128, kPairInvGroup), 64);
       F* scratch = reinterpret_cast<F*>(r->round_prefix);
       F* prod = reinterpret_cast<F*>(r->round_prod);
+      Affine<F>* ops = g_tune_pair_stage.load() ? reinterpret_cast<Affine<F>*>(r->round_ops) : nullptr;   // round 1 only;
+                                                                                   // null unless the run was created with it
 #define NZCP_PAIR_LAUNCH(TABLE, KK)                                                                                       \
       do {                                                                                                                \
-        msm_pair_forward_kernel<F, TABLE, KK><<<grid, 128, 0, st>>>(src, s->entries, off_in, off_out, nb, scratch, prod); \
+        msm_pair_forward_kernel<F, TABLE, KK><<<grid, 128, 0, st>>>(src, s->entries, off_in, off_out, nb, scratch, prod, \
+                                                                    pf_fwd, TABLE ? ops : nullptr);                       \
         NZCP_LAUNCH_CHECK();                                                                                              \
         msm_pair_invert_kernel<F, KK><<<grid_inv, 64, 0, st>>>(prod, off_out, nb);                                        \
         NZCP_LAUNCH_CHECK();                                                                                              \
         msm_pair_backward_kernel<F, TABLE, KK><<<grid, 128, 0, st>>>(src, s->entries, off_in, off_out, nb, dst, scratch,  \
-                                                                     prod);                                               \
+                                                                     prod, pf_bwd, TABLE ? ops : nullptr);                \
         NZCP_LAUNCH_CHECK();                                                                                              \
       } while (0)
       if (rd == 1) {

@@ -22,6 +22,7 @@
 #pragma once
 #include "ec.cuh"
 
+
 namespace nzcp {
 
 enum PairKind { kPairNormal = 0, kPairDouble = 1, kPairFirst = 2, kPairSecond = 3, kPairInfinity = 4 };
@@ -32,6 +33,7 @@ template <class F, bool FROM_TABLE>
 struct PairSource {
   const Affine<F>* pts;
   const uint32_t* entries;
+  int pf = 0;   // how a round asks for its next operands ahead of use: 0 = not at all (default), 1 = prefetch to L1, 2 = to L2
   HD uint32_t slot(uint32_t idx) const { return FROM_TABLE ? entries[idx] : idx; }   // table index | sign, or the index
   HD F x_at(uint32_t slot) const { return pts[FROM_TABLE ? (slot & 0x7fffffffu) : slot].x; }
   HD Affine<F> point_at(uint32_t slot) const {
@@ -43,13 +45,22 @@ struct PairSource {
     return pts[slot];
   }
   HD Affine<F> point(uint32_t idx) const { return point_at(slot(idx)); }
-  // Ask for the point's cache line ahead of its use (device only; the gathers of round 1 miss L2 four times out of five).
+  // Optionally ask for the point's cache line ahead of its use (device only).  OFF by default: measured on the B200 with
+  // four proofs in flight, the L1 prefetch of the next pair's operands COSTS 5-6 % proofs/s (124 -> 131 without it,
+  // profiles/r02_window_rounds_sweep.md): 768 resident threads x 4 lines overrun the L1 and evict lines before their use,
+  // and the extra requests queue in front of the demand loads of the kernels running beside this one.
   HD void prefetch(uint32_t slot, bool whole_point) const {
 #if defined(__CUDA_ARCH__)
+    if (pf == 0) return;
     // 64-byte granules (the points are 64-byte aligned): G1 x or whole point = 1, G2 x = 1, G2 whole point = 2
     const char* a = reinterpret_cast<const char*>(pts + (FROM_TABLE ? (slot & 0x7fffffffu) : slot));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-    if (sizeof(F) > 32 && whole_point) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 64));
+    if (pf == 1) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+      if (sizeof(F) > 32 && whole_point) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 64));
+    } else {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      if (sizeof(F) > 32 && whole_point) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 64));
+    }
 #else
     (void)slot;
     (void)whole_point;
@@ -121,9 +132,14 @@ HD void pair_walk_seek(PairWalk& wk, uint32_t o, uint32_t n_buckets) {
 // scratch: K x stride running products, element (i, t) at i * stride + t; prod[t] = product of the thread's denominators
 // (one() when it has none).  Runs one step ahead of itself: while pair i is multiplied the lines of pair i + 1 are on
 // their way to L1.
+//
+// ops (optional, round 1): the thread also writes the two whole operands of every pair to ops[2 * (i * stride + t) + {0, 1}]
+// (the second is infinity for an odd point out).  The gather from the window table has pulled their cache lines anyway;
+// the backward pass then STREAMS the operands (coalesced: adjacent threads, adjacent 128 / 256 bytes) instead of gathering
+// them a second time at random-access DRAM efficiency.
 template <class F, bool FROM_TABLE, int K>
 HD void msm_pair_forward_body(uint32_t t, uint32_t stride, const PairSource<F, FROM_TABLE>& src, const uint32_t* off_in,
-                              const uint32_t* off_out, uint32_t n_buckets, F* scratch, F* prod) {
+                              const uint32_t* off_out, uint32_t n_buckets, F* scratch, F* prod, Affine<F>* ops = nullptr) {
   uint32_t o0, cnt;
   if (!pair_thread_range<K>(t, off_out, n_buckets, o0, cnt)) return;
   PairWalk wk{off_in, off_out, 0, 0, 0, 0, 0};
@@ -138,14 +154,27 @@ HD void msm_pair_forward_body(uint32_t t, uint32_t stride, const PairSource<F, F
     if (i + 1 < cnt) {
       wk.forward_to(o0 + i + 1);
       pair_nxt = wk.paired(o0 + i + 1);
+      if (pair_nxt || ops) a_nxt = src.slot(wk.first(o0 + i + 1));   // an odd point out is only needed when it is staged
       if (pair_nxt) {
-        a_nxt = src.slot(wk.first(o0 + i + 1));
         b_nxt = src.slot(wk.first(o0 + i + 1) + 1);
         src.prefetch(a_nxt, false);
         src.prefetch(b_nxt, false);
       }
     }
-    if (pair_cur) {
+    if (ops) {
+      const Affine<F> p1 = src.point_at(a_cur);
+      const Affine<F> p2 = pair_cur ? src.point_at(b_cur) : Affine<F>::inf();
+      ops[2 * ((size_t)i * stride + t)] = p1;
+      ops[2 * ((size_t)i * stride + t) + 1] = p2;
+      if (pair_cur) {
+        F den;
+        const int kind = pair_classify(p1, p2, den);
+        if (kind == kPairNormal || kind == kPairDouble) {
+          pre = have ? f_mul(pre, den) : den;
+          have = true;
+        }
+      }
+    } else if (pair_cur) {
       const F x1 = src.x_at(a_cur), x2 = src.x_at(b_cur);
       F den = f_sub(x2, x1);
       bool use = true;
@@ -190,12 +219,43 @@ HD void msm_pair_invert_body(uint32_t g, F* v, uint32_t n) {
 }
 
 // Backward kernel body: inv_prod[t] = 1 / prod[t].
+// One affine addition (or its special cases) with the shared inverse peeled off `inv`; `before` = product of the thread's
+// denominators before this pair's.
+template <class F>
+HD Affine<F> pair_finish(const Affine<F>& p1, const Affine<F>& p2, F& inv, const F& before) {
+  F den;
+  const int kind = pair_classify(p1, p2, den);
+  if (kind >= kPairFirst) return kind == kPairFirst ? p1 : kind == kPairSecond ? p2 : Affine<F>::inf();
+  const F dinv = f_mul(inv, before);
+  inv = f_mul(inv, den);
+  F num;
+  if (kind == kPairDouble) {
+    const F xx = f_sqr(p1.x);
+    num = f_add(f_dbl(xx), xx);
+  } else {
+    num = f_sub(p2.y, p1.y);
+  }
+  const F lam = f_mul(num, dinv);
+  const F x3 = f_sub(f_sub(f_sqr(lam), p1.x), p2.x);
+  const F y3 = f_sub(f_mul(lam, f_sub(p1.x, x3)), p1.y);
+  return Affine<F>{x3, y3};
+}
+
 template <class F, bool FROM_TABLE, int K>
 HD void msm_pair_backward_body(uint32_t t, uint32_t stride, const PairSource<F, FROM_TABLE>& src, const uint32_t* off_in,
                                const uint32_t* off_out, uint32_t n_buckets, Affine<F>* dst, const F* scratch,
-                               const F* inv_prod) {
+                               const F* inv_prod, const Affine<F>* ops = nullptr) {
   uint32_t o0, cnt;
   if (!pair_thread_range<K>(t, off_out, n_buckets, o0, cnt)) return;
+  if (ops) {   // operands staged by the forward pass: no bucket walk, no gather -- an odd point out is (P, infinity) -> P
+    F inv = inv_prod[t];
+    for (uint32_t i = cnt; i-- > 0;) {
+      const Affine<F> p1 = ops[2 * ((size_t)i * stride + t)], p2 = ops[2 * ((size_t)i * stride + t) + 1];
+      const F before = i ? scratch[(size_t)(i - 1) * stride + t] : F::one();
+      dst[o0 + i] = pair_finish(p1, p2, inv, before);
+    }
+    return;
+  }
   PairWalk wk{off_in, off_out, 0, 0, 0, 0, 0};
   pair_walk_seek(wk, o0 + cnt - 1, n_buckets);
   F inv = inv_prod[t];
@@ -224,27 +284,8 @@ HD void msm_pair_backward_body(uint32_t t, uint32_t stride, const PairSource<F, 
     if (!pair_cur) {     // odd point out: carried to the next round as it is
       dst[o] = src.point_at(a_cur);
     } else {
-      const Affine<F> p1 = src.point_at(a_cur), p2 = src.point_at(b_cur);
-      F den;
-      const int kind = pair_classify(p1, p2, den);
-      if (kind >= kPairFirst) {
-        dst[o] = kind == kPairFirst ? p1 : kind == kPairSecond ? p2 : Affine<F>::inf();
-      } else {
-        const F before = i ? scratch[(size_t)(i - 1) * stride + t] : F::one();   // product of the denominators before this one
-        const F dinv = f_mul(inv, before);
-        inv = f_mul(inv, den);
-        F num;
-        if (kind == kPairDouble) {
-          const F xx = f_sqr(p1.x);
-          num = f_add(f_dbl(xx), xx);
-        } else {
-          num = f_sub(p2.y, p1.y);
-        }
-        const F lam = f_mul(num, dinv);
-        const F x3 = f_sub(f_sub(f_sqr(lam), p1.x), p2.x);
-        const F y3 = f_sub(f_mul(lam, f_sub(p1.x, x3)), p1.y);
-        dst[o] = Affine<F>{x3, y3};
-      }
+      const F before = i ? scratch[(size_t)(i - 1) * stride + t] : F::one();   // product of the denominators before this one
+      dst[o] = pair_finish(src.point_at(a_cur), src.point_at(b_cur), inv, before);
     }
     pair_cur = pair_nxt;
     a_cur = a_nxt;

@@ -271,9 +271,11 @@ static void prover_release(nzcp_prover* p) {
   delete p;
 }
 
-// mode 0 = latency (a lone proof at a time: XYZZ bucket accumulation only), mode 1 = throughput (several provers in flight:
-// the batched-affine pair rounds of msm_pair.cuh on every MSM -- their gather-bound passes overlap the multiplier-bound
-// kernels of the other proofs; measured +5 % proofs/s at +0.45 ms lone-proof latency, profiles/r02_window_rounds_sweep.md).
+// mode 0 = latency (a lone proof at a time), mode 1 = throughput (several provers in flight on one GPU).  Both run the
+// batched-affine pair rounds of msm_pair.cuh on every MSM large enough to pay for their extra launches: with the rounds'
+// operand prefetch off they cut a lone proof from 9.27 to 8.78 ms and raise four-in-flight throughput from 118 to 131
+// proofs/s (profiles/r02_window_rounds_sweep.md).  The mode is kept in the ABI for what differs between the two uses
+// (today: nothing but the name; nzcp_prove_batch creates mode-1 provers).
 static nzcp_prover* prover_create_impl(nzcp_zkey* zk, int mode = 0) {
   use_device(zk->device);
   std::unique_ptr<nzcp_prover, void (*)(nzcp_prover*)> p(new nzcp_prover(), prover_release);
@@ -290,8 +292,9 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk, int mode = 0) {
   NZCP_CUDA(cudaMalloc(&p->d_abc, 3 * n * sizeof(Fr)));
   NZCP_CUDA(cudaMalloc(&p->d_h, n * sizeof(Fr)));
   int rounds_h = g_tune_rounds_h.load(), rounds_w = g_tune_rounds_w.load();
-  if (rounds_h < 0) rounds_h = mode == 1 ? msm_pick_rounds_throughput(n, zk->c_h) : msm_pick_rounds(n, zk->c_h);
-  if (rounds_w < 0) rounds_w = mode == 1 ? msm_pick_rounds_throughput(zk->n_vars, zk->c_w) : msm_pick_rounds(zk->n_vars, zk->c_w);
+  (void)mode;
+  if (rounds_h < 0) rounds_h = msm_pick_rounds_prover(n, zk->c_h);
+  if (rounds_w < 0) rounds_w = msm_pick_rounds_prover(zk->n_vars, zk->c_w);
   msm_sort_create(&p->sort_w, zk->n_vars, zk->c_w, rounds_w);
   msm_sort_create(&p->sort_h, n, zk->c_h, rounds_h);
   msm_run_create(&p->run_a, &p->sort_w, false);

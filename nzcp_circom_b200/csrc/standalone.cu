@@ -9,6 +9,7 @@
 namespace nzcp {
 
 extern std::atomic<int> g_tune_rounds;                   // msm.cu
+extern std::atomic<int> g_tune_pair_stage;
 extern std::atomic<int> g_tune_pair_k[kMsmMaxRounds];
 extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;
 
@@ -339,10 +340,12 @@ __global__ void __launch_bounds__(256) pipeprobe_kernel(int iters, uint32_t seed
 template <class F, int K>
 static void sim_round(bool from_table, const std::vector<Affine<F>>& src, const std::vector<uint32_t>& entries,
                       const std::vector<uint32_t>& off_in, const std::vector<uint32_t>& off_out, uint32_t nb,
-                      std::vector<Affine<F>>& dst) {
+                      std::vector<Affine<F>>& dst, bool stage_ops) {
   const uint32_t n_out = off_out[nb];
   const uint32_t threads = (n_out + K - 1) / K + 3;   // a few surplus threads, as the over-sized device grid has
   std::vector<F> scratch((size_t)threads * K), prod(threads + 40, F::one());
+  std::vector<Affine<F>> ops(from_table && stage_ops ? (size_t)threads * K * 2 : 0);   // round 1: staged operands, as on the device
+  Affine<F>* opsp = ops.empty() ? nullptr : ops.data();
   dst.assign(n_out ? n_out : 1, Affine<F>::inf());
   const uint32_t n_prod = (n_out + K - 1) / K;
   for (int phase = 0; phase < 3; phase++) {
@@ -352,11 +355,11 @@ static void sim_round(bool from_table, const std::vector<Affine<F>>& src, const 
     }
     for (uint32_t t = 0; t < threads; t++) {
       if (from_table) {
-        PairSource<F, true> ps{src.data(), entries.data()};
-        if (phase == 0) msm_pair_forward_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, scratch.data(), prod.data());
-        else msm_pair_backward_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data(), prod.data());
+        PairSource<F, true> ps{src.data(), entries.data(), 0};
+        if (phase == 0) msm_pair_forward_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, scratch.data(), prod.data(), opsp);
+        else msm_pair_backward_body<F, true, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data(), prod.data(), opsp);
       } else {
-        PairSource<F, false> ps{src.data(), nullptr};
+        PairSource<F, false> ps{src.data(), nullptr, 0};
         if (phase == 0) msm_pair_forward_body<F, false, K>(t, threads, ps, off_in.data(), off_out.data(), nb, scratch.data(), prod.data());
         else msm_pair_backward_body<F, false, K>(t, threads, ps, off_in.data(), off_out.data(), nb, dst.data(), scratch.data(), prod.data());
       }
@@ -419,13 +422,14 @@ static XYZZ<F> host_msm_sim(const uint8_t* bases, const uint8_t* scalars, size_t
   }
   entries.push_back(0);
   std::vector<Affine<F>> cur, nxt;
+  const bool stage = g_tune_pair_stage.load() != 0;   // "pair_stage" knob, as the device path reads it
   for (int r = 1; r <= rounds; r++) {
     const std::vector<Affine<F>>& src = r == 1 ? table : cur;
     switch (k) {
-      case 4: sim_round<F, 4>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
-      case 16: sim_round<F, 16>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
-      case 32: sim_round<F, 32>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
-      case 8: sim_round<F, 8>(r == 1, src, entries, off[r - 1], off[r], nb, nxt); break;
+      case 4: sim_round<F, 4>(r == 1, src, entries, off[r - 1], off[r], nb, nxt, stage); break;
+      case 16: sim_round<F, 16>(r == 1, src, entries, off[r - 1], off[r], nb, nxt, stage); break;
+      case 32: sim_round<F, 32>(r == 1, src, entries, off[r - 1], off[r], nb, nxt, stage); break;
+      case 8: sim_round<F, 8>(r == 1, src, entries, off[r - 1], off[r], nb, nxt, stage); break;
       default: throw ApiError(NZCP_E_ARG, "additions per thread must be 4, 8, 16 or 32");
     }
     cur.swap(nxt);

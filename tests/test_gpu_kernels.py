@@ -247,7 +247,7 @@ def forced_rounds():
             api.tuning_set(name, k)
     yield force
     for name, v in (("msm_rounds", -1), ("prover_rounds_w", -1), ("prover_rounds_h", -1), ("pair_k1", 16), ("pair_k2", 16),
-                    ("pair_k3", 16)):
+                    ("pair_k3", 16), ("pair_stage", 0), ("pair_prefetch_fwd", 0), ("pair_prefetch_bwd", 0)):
         api.tuning_set(name, v)
 
 
@@ -274,11 +274,16 @@ def test_msm_pair_rounds_forced_edge_cases(lib, fixed_bases, forced_rounds, g2, 
     _msm_case(g2, [P], [R - 1])
 
 
+@pytest.mark.parametrize("stage", [1, 0])
 @pytest.mark.parametrize("rounds", [1, 2, 3])
-def test_msm_pair_rounds_forced_mid_size(lib, forced_rounds, rounds):
-    """2^13 points, witness-like scalars (heavy bucket "1"), vs the C oracle, every round count."""
+def test_msm_pair_rounds_forced_mid_size(lib, forced_rounds, rounds, stage):
+    """2^13 points, witness-like scalars (heavy bucket "1"), vs the C oracle, every round count; round 1 with its operands
+    gathered twice (default) and staged by the forward pass ("pair_stage" = 1), with and without operand prefetch."""
     from oracle import cref
     forced_rounds(rounds, 32)
+    api.tuning_set("pair_stage", stage)
+    api.tuning_set("pair_prefetch_fwd", 1 - stage)
+    api.tuning_set("pair_prefetch_bwd", 2 * (1 - stage))
     n = 1 << 13
     bases = bytes(api.synth_points(9, n))
     rng = random.Random(12)

@@ -36,13 +36,20 @@ def fixed_bases():
 
 
 def _check(g2, pts, scalars, c, rounds, k):
+    """Both round-1 variants: operands gathered a second time from the window table by the backward pass (the default), and
+    staged by the forward pass / streamed by the backward pass ("pair_stage" = 1)."""
     curve = ob.G2 if g2 else ob.G1
     enc = ob.g2_to_bytes_mont if g2 else ob.g1_to_bytes_mont
     bases = b"".join(enc(P) for P in pts)
     sc = b"".join(le32(s) for s in scalars)
-    got = api.host_msm_sim(bases, sc, len(pts), g2=g2, window_bits=c, rounds=rounds, adds_per_thread=k)
     exp = curve.to_affine(oprover.multiexp(curve, pts, scalars))
-    assert got == (g2_plain_bytes(exp) if g2 else g1_plain_bytes(exp)), (g2, c, rounds, k)
+    try:
+        for stage in (1, 0):
+            api.tuning_set("pair_stage", stage)
+            got = api.host_msm_sim(bases, sc, len(pts), g2=g2, window_bits=c, rounds=rounds, adds_per_thread=k)
+            assert got == (g2_plain_bytes(exp) if g2 else g1_plain_bytes(exp)), (g2, c, rounds, k, stage)
+    finally:
+        api.tuning_set("pair_stage", 0)
 
 
 @pytest.mark.parametrize("g2", [False, True])
