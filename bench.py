@@ -335,7 +335,7 @@ def main():
     lat_pageable, lat[:] = list(lat[5:]), lat_pinned
 
     # per-stage device times + the dominant kernel, from the library's own CUDA events (one extra proof, not timed above)
-    dbg = pr.prove_device(d_wit[0], r=R_FIXED, s=S_FIXED, debug=True)
+    dbg = pr.prove(host_wtns[0], r=R_FIXED, s=S_FIXED, debug=True, want_h=True)
     correct = None
     value = world * B * args.steps / (ms_dev / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
@@ -367,7 +367,7 @@ def main():
         }
         if args.tune:
             line["config"]["tune"] = args.tune
-        line.update(roofline_block(dbg, zk, hbm, peak_src))
+        line.update(roofline_block(dbg, zk, hbm, peak_src, zkey, dbg.pop("h", None)))
         line["roofline_step"] = step_roofline(dbg, zk, value / world, line["roofline"]["peak"] if "roofline" in line else None)
         line["modes"] = ("value / e2e: %d throughput-mode provers in flight (batched-affine pair rounds on); "
                                    "p50_latency_ms, stage_ms, roofline: one latency-mode prover, lone proofs" % args.provers)
@@ -530,42 +530,91 @@ def step_roofline(dbg, zk, proofs_per_s_per_gpu, peak_gmul):
     return out
 
 
-def roofline_block(dbg, zk, hbm, peak_src):
-    """Roofline of the dominant kernel -- from the library's live CUDA-event timings on the kernel's own stream.
+def zkey_section(zkey, sid):
+    """Payload of section `sid` of a .zkey image (binfileutils container)."""
+    import struct
+    mv = memoryview(zkey)
+    pos = 12
+    for _ in range(struct.unpack_from("<I", mv, 8)[0]):
+        i, ln = struct.unpack_from("<IQ", mv, pos)
+        pos += 12
+        if i == sid:
+            return mv[pos:pos + ln]
+        pos += ln
+    raise KeyError(sid)
 
-    The dominant kernel is the bucket-accumulate of the H MSM (msm_accumulate_kernel<Fq>): it is bound by the 32-bit
-    integer multiply pipe, not by HBM or the tensor cores (DESIGN.md "Rooflines").  Algorithmic work per launch =
-    (non-zero signed digits of the h scalars) x 10 Fq products (8M + 2S mixed addition).  Peak = the
-    IMAD.WIDE.U32 issue rate measured on this GPU by nzcp_intpipe_bench / 128 products per Montgomery multiplication
-    (the MEASURED_PEAKS.json file has no integer figure; bound names follow DESIGN.md, not the hbm|tensor pair).
+
+def h_stage_alone(zkey, zk, h_scalars):
+    """The H MSM's bucket accumulation with the GPU to itself: the same kernels the prover runs (fixed-base window table of
+    zkey section 9, c = 16; 3 batched-affine pair rounds + XYZZ tail), on the h scalars of a real proof, timed by the
+    library's CUDA events around the accumulation on its own stream.  Also the single XYZZ kernel (rounds off)."""
+    from nzcp_circom_b200 import api
+    n = zk.domain_size
+    out = {}
+    try:
+        for rounds, key in ((3, "pair_rounds"), (0, "xyzz_only")):
+            api.tuning_set("msm_rounds", rounds)
+            with api.MsmPlan(zkey_section(zkey, 9), n, mode=0, window_bits=16, device=zk.device) as plan:
+                plan.run(h_scalars)
+                ts = []
+                for _ in range(5):
+                    plan.run(h_scalars)
+                    ts.append(plan.accumulate_ms())
+                out[key] = sum(ts) / len(ts)
+    finally:
+        api.tuning_set("msm_rounds", -1)
+    return out
+
+
+def roofline_block(dbg, zk, hbm, peak_src, zkey=None, h_scalars=None):
+    """Roofline of the dominant kernel group -- from the library's live CUDA-event timings on the kernels' own stream.
+
+    The dominant work of the step is the bucket accumulation of the H MSM.  In the default configuration that is three
+    batched-affine pair rounds (msm_pair_forward / invert / backward_kernel<Fq>, 9 launches) followed by the XYZZ tail
+    (msm_accumulate_pts_kernel<Fq>): ten launches timed as ONE unit.  It is scored against the integer multiply pipe, not
+    HBM or the tensor cores (DESIGN.md "Rooflines"): algorithmic work = (non-zero signed digits of the h scalars) x 10 Fq
+    products (the CANONICAL 8M + 2S mixed addition of SURVEY.md 8d; the pair rounds execute ~6.3 per addition, so the
+    fraction credits that saving, as the survey prescribes).  Peak = the IMAD.WIDE.U32 issue rate measured on this GPU
+    by nzcp_intpipe_bench / 128 products per Montgomery multiplication (MEASURED_PEAKS.json has no integer figure).
+    `launch_ms` = the unit timed ALONE on the GPU (average of 5; what the ncu launch list shows as well); `in_proof_ms` =
+    the same unit inside a lone proof, where it shares the SMs with the four witness MSMs.
     """
     from nzcp_circom_b200 import api
     out = {}
     ip = api.intpipe_bench(zk.device, 4096)
     peak_mul = ip["imad_wide_per_s"] / 128.0
-    acc_ms = dbg["accumulate_ms"]["h"]
+    in_proof_ms = dbg["accumulate_ms"]["h"]
     ent = dbg["n_entries"]["h"]
+    alone = h_stage_alone(zkey, zk, h_scalars) if zkey is not None and h_scalars is not None else {}
+    acc_ms = alone.get("pair_rounds") or in_proof_ms
     if acc_ms > 0:
         ach = ent * 10 / (acc_ms * 1e-3)
         alg_bytes = ent * (64 + 4) + (ent / 64.0) * 128
         out["roofline"] = {
-            "kernel": "msm_accumulate_kernel<Fq> (H MSM bucket accumulation)", "bound": "int32-mul-pipe",
+            "kernel": "H MSM bucket accumulation: 3 batched-affine pair rounds (msm_pair_forward/invert/backward_kernel<Fq>) + "
+                      "XYZZ tail (msm_accumulate_pts_kernel<Fq>), 10 launches timed as one unit",
+            "bound": "int32-mul-pipe",
             "achieved": ach / 1e9, "peak": peak_mul / 1e9, "unit": "GFqmul/s", "frac": ach / peak_mul,
-            "traffic": 2.29e9 * ent / 16776933.0,
-            "traffic_source": "recorded, not live: dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed "
-                              "ncu --set full capture profiles/r01_ncu_accumulate_ntt_full.md (2.29 GB at 16 776 933 entries), "
-                              "scaled by this run's entry count",
-            "launch_ms": acc_ms, "algorithmic_fq_mul": ent * 10,
-            "traffic_note": "ncu --set full (profiles/r01_ncu_accumulate_ntt_full.md): dram read+write 2.29 GB per launch vs "
-                            "1.14 GB algorithmic (68 B/entry): 64-B points fetched as 128-B lines; DRAM at 10 % of peak, "
-                            "fmaheavy (IMAD.WIDE) pipe 85 % active -- the kernel sits on the multiplier, not on memory",
+            "launch_ms": acc_ms, "in_proof_ms": in_proof_ms, "algorithmic_fq_mul": ent * 10,
+            "traffic": 8.0e9 * ent / 16776933.0,
+            "traffic_source": "recorded, not live: dram__bytes_read.sum + dram__bytes_write.sum of the unit's ten launches in the "
+                              "committed ncu launch list profiles/r02_launches_pipe_final.csv (6.69 GB read + 1.31 GB written at "
+                              "16 776 933 entries), scaled by this run's entry count; algorithmic bytes: 1.14 GB (68 B/entry) -- "
+                              "an affine addition reads each operand twice and the rounds write their sums back",
             "peak_source": "measured here: %.2f T IMAD.WIDE.U32/s (32 per SM per clock, half the 32-bit IMAD rate) / 128 "
                            "32x32 products per 254-bit Montgomery mul; a register-only Fq mul microbenchmark reaches "
                            "%.1f GFqmul/s" % (ip["imad_wide_per_s"] / 1e12, ip["fq_mul_per_s"] / 1e9),
-            "hbm_view": {"bound": "hbm", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm,
-                         "note": "68 B per entry (64 B table point + 4 B index) + 128 B per 64-entry task; peak %s" % peak_src},
+            "hbm_view": {"bound": "hbm", "achieved": 8.0e9 * ent / 16776933.0 / (acc_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": 8.0e9 * ent / 16776933.0 / (acc_ms * 1e-3) / 1e9 / hbm,
+                         "note": "recorded DRAM traffic of the unit / its live duration; algorithmic bytes (%.2f GB) would give %.0f GB/s; "
+                                 "peak %s" % (alg_bytes / 1e9, alg_bytes / (acc_ms * 1e-3) / 1e9, peak_src)},
         }
+        if alone.get("xyzz_only"):
+            x = alone["xyzz_only"]
+            out["roofline"]["xyzz_kernel"] = {
+                "kernel": "msm_accumulate_kernel<Fq> (the single-kernel alternative: XYZZ mixed additions only, pair rounds off)",
+                "launch_ms": x, "achieved": ent * 10 / (x * 1e-3) / 1e9, "frac": ent * 10 / (x * 1e-3) / peak_mul,
+                "note": "executes the canonical 10 products per addition; fmaheavy 85 % active (profiles/r02_ncu_ntt_accumulate_full.md)"}
     # the NTT pipeline: 3 polynomials x (iNTT + NTT) = 6 transforms x 2 x 32 x n bytes
     n = zk.domain_size
     ntt_ms = dbg["stage_ms"].get("ntt_join")

@@ -180,6 +180,8 @@ int nzcp_msm_plan_create(const uint8_t* bases, size_t n_points, int g2, int wind
                          nzcp_msm_plan** out, float* build_ms);
 void nzcp_msm_plan_free(nzcp_msm_plan* p);
 int nzcp_msm_plan_run(nzcp_msm_plan* p, const uint8_t* scalars, size_t n_scalars, uint8_t* out, float* kernel_ms);
+/* Device time of the bucket accumulation alone (pair rounds + XYZZ kernel) in the plan's last run. */
+int nzcp_msm_plan_accumulate_ms(const nzcp_msm_plan* p, float* ms);
 /* Split MSM (BASELINE.json configs[4]): the result stays in HBM as ONE extended-Jacobian point (x, y, zz,
  * zzz Montgomery: 128 B for G1, 256 B for G2) written to the device pointer d_out, e.g. this rank's slot of an NCCL
  * all-gather buffer.  nzcp_msm_sum_partials then adds `count` such points on the GPU and returns the plain affine sum. */

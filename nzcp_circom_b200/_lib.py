@@ -78,6 +78,7 @@ SIGNATURES = {
                                        C.POINTER(C.c_float)]),
     "nzcp_msm_plan_free": (None, [_P]),
     "nzcp_msm_plan_run": (C.c_int, [_P, _U8P, C.c_size_t, _U8P, C.POINTER(C.c_float)]),
+    "nzcp_msm_plan_accumulate_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "nzcp_msm_plan_run_partial": (C.c_int, [_P, _U8P, C.c_size_t, _P, C.POINTER(C.c_float)]),
     "nzcp_msm_sum_partials": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, _U8P]),
     "nzcp_msm_var": (C.c_int, [_U8P, _U8P, C.c_size_t, C.c_int, C.c_int, C.c_int, _U8P, C.POINTER(C.c_float)]),

@@ -284,6 +284,12 @@ class MsmPlan:
         check(_lib.load().nzcp_msm_plan_run(self._h, addr(scalars) if n else None, n, addr(out), C.byref(ms)))
         return bytes(out), ms.value
 
+    def accumulate_ms(self):
+        """Device time of the bucket accumulation alone (pair rounds + XYZZ kernel) in the last run."""
+        ms = C.c_float()
+        check(_lib.load().nzcp_msm_plan_accumulate_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def run_partial(self, scalars, d_out, n_scalars=None):
         n = self.n_points if n_scalars is None else int(n_scalars)
         ms = C.c_float()

@@ -140,6 +140,14 @@ int nzcp_msm_plan_run(nzcp_msm_plan* p, const uint8_t* scalars, size_t n_scalars
   });
 }
 
+/* Device time of the bucket accumulation (pair rounds + XYZZ kernel) of the plan's last run, CUDA events on its stream. */
+int nzcp_msm_plan_accumulate_ms(const nzcp_msm_plan* p, float* ms) {
+  return api_guard([&] {
+    if (!p || !ms) throw ApiError(NZCP_E_ARG, "null argument");
+    *ms = msm_run_accumulate_ms(&p->run);
+  });
+}
+
 int nzcp_msm_plan_run_partial(nzcp_msm_plan* p, const uint8_t* scalars, size_t n_scalars, void* d_out, float* kernel_ms) {
   return api_guard([&] {
     if (!p || !d_out) throw ApiError(NZCP_E_ARG, "null argument");
