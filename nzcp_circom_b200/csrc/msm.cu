@@ -505,7 +505,7 @@ template <class F, int K>
 __global__ void __launch_bounds__(64)
 msm_pair_invert_kernel(F* __restrict__ prod, const uint32_t* __restrict__ off_out, uint32_t n_buckets) {
   const uint32_t n_out = off_out[n_buckets];
-  const uint32_t n_prod = (n_out + K - 1) / K;      // threads of the forward kernel that had work
+  const uint32_t n_prod = pair_n_prod<K>(n_out);    // threads of the forward kernel that had work
   msm_pair_invert_body<F, kPairInvGroup>(blockIdx.x * blockDim.x + threadIdx.x, prod, n_prod);
 }
 
@@ -1115,7 +1115,7 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
       const int pf_fwd = g_tune_pair_prefetch[0].load(), pf_bwd = g_tune_pair_prefetch[1].load();
       int k = g_tune_pair_k[rd - 1].load();
       k = k >= 32 ? 32 : k >= 16 ? 16 : k >= 8 ? 8 : 4;
-      const unsigned grid = div_up(div_up(s->round_max[rd], k), 128);
+      const unsigned grid = div_up(div_up(s->round_max[rd], k) + kPairLanes, 128);   // + one warp: the last one may be partial in every lane
       const unsigned grid_inv = div_up(div_up((size_t)grid * 128, kPairInvGroup), 64);
       F* scratch = reinterpret_cast<F*>(r->round_prefix);
       F* prod = reinterpret_cast<F*>(r->round_prod);

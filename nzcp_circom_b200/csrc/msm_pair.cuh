@@ -109,14 +109,27 @@ HD int pair_classify(const Affine<F>& p1, const Affine<F>& p2, F& den) {
   return kPairNormal;
 }
 
-// The pairs of thread t: outputs [t * K, t * K + K) of the round.
+// The pairs of thread t.  The K outputs of a thread are INTERLEAVED across its warp: warp w owns the outputs
+// [w * 32 K, (w + 1) * 32 K) and lane l takes w * 32 K + i * 32 + l, i < K -- at every step the 32 lanes touch 32
+// consecutive outputs, so the entry list, the previous round's point array and the round's own output are read and
+// written as contiguous 2-4 KB runs per warp instead of 32 scattered lines (a thread's K pairs need not be adjacent:
+// Montgomery's trick only wants them to be the same pairs in the forward and the backward pass).
+static constexpr uint32_t kPairLanes = 32;
 template <int K>
 HD bool pair_thread_range(uint32_t t, const uint32_t* off_out, uint32_t n_buckets, uint32_t& o0, uint32_t& cnt) {
   const uint32_t n_out = off_out[n_buckets];
-  if ((uint64_t)t * K >= n_out) return false;
-  o0 = t * K;
-  cnt = n_out - o0 < (uint32_t)K ? n_out - o0 : (uint32_t)K;
+  const uint64_t first = (uint64_t)(t / kPairLanes) * (kPairLanes * K) + (t % kPairLanes);
+  if (first >= n_out) return false;
+  o0 = (uint32_t)first;
+  const uint32_t left = (n_out - o0 + kPairLanes - 1) / kPairLanes;
+  cnt = left < (uint32_t)K ? left : (uint32_t)K;
   return true;
+}
+// Threads 0 .. pair_n_prod - 1 are exactly the ones with work (and a denominator product to invert).
+template <int K>
+HD uint32_t pair_n_prod(uint32_t n_out) {
+  const uint32_t full = n_out / (kPairLanes * K), rem = n_out - full * (kPairLanes * K);
+  return full * kPairLanes + (rem < kPairLanes ? rem : kPairLanes);
 }
 HD void pair_walk_seek(PairWalk& wk, uint32_t o, uint32_t n_buckets) {
   uint32_t lo = 0, hi = n_buckets;   // off_out[lo] <= o < off_out[hi]
@@ -152,11 +165,12 @@ HD void msm_pair_forward_body(uint32_t t, uint32_t stride, const PairSource<F, F
     bool pair_nxt = false;
     uint32_t a_nxt = 0, b_nxt = 0;
     if (i + 1 < cnt) {
-      wk.forward_to(o0 + i + 1);
-      pair_nxt = wk.paired(o0 + i + 1);
-      if (pair_nxt || ops) a_nxt = src.slot(wk.first(o0 + i + 1));   // an odd point out is only needed when it is staged
+      const uint32_t on = o0 + (i + 1) * kPairLanes;
+      wk.forward_to(on);
+      pair_nxt = wk.paired(on);
+      if (pair_nxt || ops) a_nxt = src.slot(wk.first(on));   // an odd point out is only needed when it is staged
       if (pair_nxt) {
-        b_nxt = src.slot(wk.first(o0 + i + 1) + 1);
+        b_nxt = src.slot(wk.first(on) + 1);
         src.prefetch(a_nxt, false);
         src.prefetch(b_nxt, false);
       }
@@ -252,32 +266,32 @@ HD void msm_pair_backward_body(uint32_t t, uint32_t stride, const PairSource<F, 
     for (uint32_t i = cnt; i-- > 0;) {
       const Affine<F> p1 = ops[2 * ((size_t)i * stride + t)], p2 = ops[2 * ((size_t)i * stride + t) + 1];
       const F before = i ? scratch[(size_t)(i - 1) * stride + t] : F::one();
-      dst[o0 + i] = pair_finish(p1, p2, inv, before);
+      dst[o0 + i * kPairLanes] = pair_finish(p1, p2, inv, before);
     }
     return;
   }
   PairWalk wk{off_in, off_out, 0, 0, 0, 0, 0};
-  pair_walk_seek(wk, o0 + cnt - 1, n_buckets);
+  pair_walk_seek(wk, o0 + (cnt - 1) * kPairLanes, n_buckets);
   F inv = inv_prod[t];
   bool pair_cur;
   uint32_t a_cur, b_cur;
   {
-    const uint32_t o = o0 + cnt - 1;
+    const uint32_t o = o0 + (cnt - 1) * kPairLanes;
     pair_cur = wk.paired(o);
     a_cur = src.slot(wk.first(o));
     b_cur = pair_cur ? src.slot(wk.first(o) + 1) : 0;
   }
   for (uint32_t i = cnt; i-- > 0;) {
-    const uint32_t o = o0 + i;
+    const uint32_t o = o0 + i * kPairLanes;
     bool pair_nxt = false;
     uint32_t a_nxt = 0, b_nxt = 0;
     if (i > 0) {
-      wk.backward_to(o - 1);
-      pair_nxt = wk.paired(o - 1);
-      a_nxt = src.slot(wk.first(o - 1));
+      wk.backward_to(o - kPairLanes);
+      pair_nxt = wk.paired(o - kPairLanes);
+      a_nxt = src.slot(wk.first(o - kPairLanes));
       src.prefetch(a_nxt, true);
       if (pair_nxt) {
-        b_nxt = src.slot(wk.first(o - 1) + 1);
+        b_nxt = src.slot(wk.first(o - kPairLanes) + 1);
         src.prefetch(b_nxt, true);
       }
     }

@@ -342,12 +342,12 @@ static void sim_round(bool from_table, const std::vector<Affine<F>>& src, const 
                       const std::vector<uint32_t>& off_in, const std::vector<uint32_t>& off_out, uint32_t nb,
                       std::vector<Affine<F>>& dst, bool stage_ops) {
   const uint32_t n_out = off_out[nb];
-  const uint32_t threads = (n_out + K - 1) / K + 3;   // a few surplus threads, as the over-sized device grid has
+  const uint32_t threads = pair_n_prod<K>(n_out) + 3;   // a few surplus threads, as the over-sized device grid has
   std::vector<F> scratch((size_t)threads * K), prod(threads + 40, F::one());
   std::vector<Affine<F>> ops(from_table && stage_ops ? (size_t)threads * K * 2 : 0);   // round 1: staged operands, as on the device
   Affine<F>* opsp = ops.empty() ? nullptr : ops.data();
   dst.assign(n_out ? n_out : 1, Affine<F>::inf());
-  const uint32_t n_prod = (n_out + K - 1) / K;
+  const uint32_t n_prod = pair_n_prod<K>(n_out);
   for (int phase = 0; phase < 3; phase++) {
     if (phase == 1) {
       for (uint32_t g = 0; g * 32 < n_prod + 64; g++) msm_pair_invert_body<F, 32>(g, prod.data(), n_prod);
