@@ -596,16 +596,16 @@ def roofline_block(dbg, zk, hbm, peak_src, zkey=None, h_scalars=None):
             "bound": "int32-mul-pipe",
             "achieved": ach / 1e9, "peak": peak_mul / 1e9, "unit": "GFqmul/s", "frac": ach / peak_mul,
             "launch_ms": acc_ms, "in_proof_ms": in_proof_ms, "algorithmic_fq_mul": ent * 10,
-            "traffic": 8.0e9 * ent / 16776933.0,
+            "traffic": 7.86e9 * ent / 16776933.0,
             "traffic_source": "recorded, not live: dram__bytes_read.sum + dram__bytes_write.sum of the unit's ten launches in the "
-                              "committed ncu launch list profiles/r02_launches_pipe_final.csv (6.69 GB read + 1.31 GB written at "
+                              "committed ncu launch list profiles/r02_launches_pipe_final.csv (6.54 GB read + 1.32 GB written at "
                               "16 776 933 entries), scaled by this run's entry count; algorithmic bytes: 1.14 GB (68 B/entry) -- "
                               "an affine addition reads each operand twice and the rounds write their sums back",
             "peak_source": "measured here: %.2f T IMAD.WIDE.U32/s (32 per SM per clock, half the 32-bit IMAD rate) / 128 "
                            "32x32 products per 254-bit Montgomery mul; a register-only Fq mul microbenchmark reaches "
                            "%.1f GFqmul/s" % (ip["imad_wide_per_s"] / 1e12, ip["fq_mul_per_s"] / 1e9),
-            "hbm_view": {"bound": "hbm", "achieved": 8.0e9 * ent / 16776933.0 / (acc_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": 8.0e9 * ent / 16776933.0 / (acc_ms * 1e-3) / 1e9 / hbm,
+            "hbm_view": {"bound": "hbm", "achieved": 7.86e9 * ent / 16776933.0 / (acc_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": 7.86e9 * ent / 16776933.0 / (acc_ms * 1e-3) / 1e9 / hbm,
                          "note": "recorded DRAM traffic of the unit / its live duration; algorithmic bytes (%.2f GB) would give %.0f GB/s; "
                                  "peak %s" % (alg_bytes / 1e9, alg_bytes / (acc_ms * 1e-3) / 1e9, peak_src)},
         }
