@@ -455,14 +455,16 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
   uint2 tk = tasks[t];
   XYZZ<F> acc = XYZZ<F>::inf();
   uint32_t e = entries[tk.x];
-  if (pf) prefetch_l1(table + (e & 0x7fffffffu));
+  if (pf & 1) prefetch_l1(table + (e & 0x7fffffffu));
   for (uint32_t k = 0; k < tk.y; k++) {
     uint32_t en = e;
     if (k + 1 < tk.y) {
       en = entries[tk.x + k + 1];
-      if (pf) prefetch_l1(table + (en & 0x7fffffffu));
+      if (pf & 1) prefetch_l1(table + (en & 0x7fffffffu));
     }
-    Affine<F> q = table[e & 0x7fffffffu];
+    Affine<F> q;
+    if (sizeof(F) == sizeof(Fq) && (pf & 4)) q = gather_hinted<Affine<F>>(table + (e & 0x7fffffffu));   // "gather_hint": see msm_pair.cuh
+    else q = table[e & 0x7fffffffu];
     if (!q.is_inf()) xyzz_madd(acc, q, (e >> 31) != 0);
     e = en;
   }
@@ -829,6 +831,7 @@ std::atomic<int> g_tune_pair_prefetch[2] = {{0}, {0}};   // forward / backward p
 // profiles/r02_window_rounds_sweep.md) -- the 2 x 1 GB of extra streaming per H MSM and a forward pass that now carries
 // whole points through its registers cost more than the second gather saves.  Kept as an opt-in, off by default.
 std::atomic<int> g_tune_pair_stage{0};
+std::atomic<int> g_tune_gather_hint{0};                  // experiment: .L2::64B fetch-size qualifier on the round-1 gathers
 std::atomic<int> g_tune_acc_prefetch{1};                 // XYZZ accumulate kernel: prefetch the next table point to L1
 
 // Pair rounds are OFF for the standalone MSMs unless asked for (nzcp_tuning_set "msm_rounds"); provers turn them on
@@ -1103,7 +1106,7 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
   if (s->rounds == 0) {
     msm_accumulate_kernel<F><<<div_up(s->max_tasks, 128), 128, 0, st>>>(reinterpret_cast<const Affine<F>*>(t->pts),
                                                                        s->entries, s->tasks, s->flags, partial,
-                                                                       g_tune_acc_prefetch.load());
+                                                                       (g_tune_acc_prefetch.load() ? 1 : 0) | (g_tune_gather_hint.load() ? 4 : 0));
     NZCP_LAUNCH_CHECK();
   } else {
     // pair rounds: table -> pts[0] -> pts[1] -> pts[0]; then the XYZZ accumulation over the last array
@@ -1112,7 +1115,8 @@ static void msm_run_launch_t(MsmRun* r, const MsmSort* s, const MsmTable* t, cud
       Affine<F>* dst = reinterpret_cast<Affine<F>*>(r->round_pts[(rd - 1) & 1]);
       const uint32_t* off_in = s->round_off + (size_t)(rd - 1) * (nb + 1);
       const uint32_t* off_out = s->round_off + (size_t)rd * (nb + 1);
-      const int pf_fwd = g_tune_pair_prefetch[0].load(), pf_bwd = g_tune_pair_prefetch[1].load();
+      const int hint = g_tune_gather_hint.load() ? 4 : 0;
+      const int pf_fwd = g_tune_pair_prefetch[0].load() | hint, pf_bwd = g_tune_pair_prefetch[1].load() | hint;
       int k = g_tune_pair_k[rd - 1].load();
       k = k >= 32 ? 32 : k >= 16 ? 16 : k >= 8 ? 8 : 4;
       const unsigned grid = div_up(div_up(s->round_max[rd], k) + kPairLanes, 128);   // + one warp: the last one may be partial in every lane

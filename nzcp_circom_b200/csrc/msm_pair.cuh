@@ -27,18 +27,46 @@ namespace nzcp {
 
 enum PairKind { kPairNormal = 0, kPairDouble = 1, kPairFirst = 2, kPairSecond = 3, kPairInfinity = 4 };
 
+#if defined(__CUDA_ARCH__)
+// Read-only 16-byte loads with the .L2::64B fetch-size qualifier (T: a multiple of 16 bytes, 16-byte aligned).
+template <class T>
+__device__ __forceinline__ T gather_hinted(const T* p) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  T r;
+  uint4* d = reinterpret_cast<uint4*>(&r);
+  const char* a = reinterpret_cast<const char*>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++)
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d[i].x), "=r"(d[i].y), "=r"(d[i].z), "=r"(d[i].w) : "l"(a + 16 * i));
+  return r;
+}
+#endif
+
 // Where a round reads its points: round 1 gathers from the window table through the sorted entry list (index | sign
 // << 31), later rounds read the previous round's array directly.
 template <class F, bool FROM_TABLE>
 struct PairSource {
   const Affine<F>* pts;
   const uint32_t* entries;
-  int pf = 0;   // how a round asks for its next operands ahead of use: 0 = not at all (default), 1 = prefetch to L1, 2 = to L2
+  int pf = 0;   // bits 0-1: how a round asks for its next operands ahead of use: 0 = not at all (default), 1 = prefetch to
+                // L1, 2 = to L2; bit 2: fetch-size hint on the table gathers (experiment)
   HD uint32_t slot(uint32_t idx) const { return FROM_TABLE ? entries[idx] : idx; }   // table index | sign, or the index
-  HD F x_at(uint32_t slot) const { return pts[FROM_TABLE ? (slot & 0x7fffffffu) : slot].x; }
+  // Gathers from the window table.  pf & 4 (experiment knob "gather_hint"): the loads carry the PTX .L2::64B fetch-size
+  // qualifier, to find out whether the 128 bytes of DRAM traffic per gathered 64-byte point are a fetch-size default.
+  HD F x_at(uint32_t slot) const {
+#if defined(__CUDA_ARCH__)
+    if (FROM_TABLE && (pf & 4)) return gather_hinted<F>(&pts[slot & 0x7fffffffu].x);
+#endif
+    return pts[FROM_TABLE ? (slot & 0x7fffffffu) : slot].x;
+  }
   HD Affine<F> point_at(uint32_t slot) const {
     if (FROM_TABLE) {
-      Affine<F> p = pts[slot & 0x7fffffffu];
+      Affine<F> p;
+#if defined(__CUDA_ARCH__)
+      if (pf & 4) p = gather_hinted<Affine<F>>(&pts[slot & 0x7fffffffu]);
+      else
+#endif
+        p = pts[slot & 0x7fffffffu];
       if (slot >> 31) p.y = f_neg(p.y);
       return p;
     }
@@ -51,10 +79,10 @@ struct PairSource {
   // and the extra requests queue in front of the demand loads of the kernels running beside this one.
   HD void prefetch(uint32_t slot, bool whole_point) const {
 #if defined(__CUDA_ARCH__)
-    if (pf == 0) return;
+    if ((pf & 3) == 0) return;
     // 64-byte granules (the points are 64-byte aligned): G1 x or whole point = 1, G2 x = 1, G2 whole point = 2
     const char* a = reinterpret_cast<const char*>(pts + (FROM_TABLE ? (slot & 0x7fffffffu) : slot));
-    if (pf == 1) {
+    if ((pf & 3) == 1) {
       asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
       if (sizeof(F) > 32 && whole_point) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 64));
     } else {

@@ -247,7 +247,7 @@ def forced_rounds():
             api.tuning_set(name, k)
     yield force
     for name, v in (("msm_rounds", -1), ("prover_rounds_w", -1), ("prover_rounds_h", -1), ("pair_k1", 16), ("pair_k2", 16),
-                    ("pair_k3", 16), ("pair_stage", 0), ("pair_prefetch_fwd", 0), ("pair_prefetch_bwd", 0)):
+                    ("pair_k3", 16), ("pair_stage", 0), ("pair_prefetch_fwd", 0), ("pair_prefetch_bwd", 0), ("gather_hint", 0)):
         api.tuning_set(name, v)
 
 
@@ -284,6 +284,7 @@ def test_msm_pair_rounds_forced_mid_size(lib, forced_rounds, rounds, stage):
     api.tuning_set("pair_stage", stage)
     api.tuning_set("pair_prefetch_fwd", 1 - stage)
     api.tuning_set("pair_prefetch_bwd", 2 * (1 - stage))
+    api.tuning_set("gather_hint", 1 - stage)          # the fetch-size-qualified gathers ride along with the second variant
     n = 1 << 13
     bases = bytes(api.synth_points(9, n))
     rng = random.Random(12)
