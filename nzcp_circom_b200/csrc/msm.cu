@@ -463,8 +463,11 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
       if (pf & 1) prefetch_l1(table + (en & 0x7fffffffu));
     }
     Affine<F> q;
+#if defined(__CUDA_ARCH__)
     if (sizeof(F) == sizeof(Fq) && (pf & 4)) q = gather_hinted<Affine<F>>(table + (e & 0x7fffffffu));   // "gather_hint": see msm_pair.cuh
-    else q = table[e & 0x7fffffffu];
+    else
+#endif
+      q = table[e & 0x7fffffffu];
     if (!q.is_inf()) xyzz_madd(acc, q, (e >> 31) != 0);
     e = en;
   }
