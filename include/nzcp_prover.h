@@ -204,6 +204,7 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
  *   "pair_prefetch_fwd" / "pair_prefetch_bwd"  operand prefetch in the pair-round kernels: 0 = none (default), 1 = L1, 2 = L2
  *   "pair_stage"  1 = round 1's forward pass stages the operands it gathered and the backward pass streams them (set it before
  *                 the prover / plan is created); 0 (default) = the backward pass gathers them from the window table again
+ *   "sort_threads"  threads per block of the bucket sort's shared-memory histogram passes: 1024 (default), 512, 256, 128
  *   "gather_hint"  experiment: 1 = the round-1 table gathers carry the PTX .L2::64B fetch-size qualifier (default 0)
  *   "acc_prefetch"  1 (default) = the XYZZ accumulate kernel prefetches its next table point to L1, 0 = no prefetch
  *   "stage_mode"  host witness upload in nzcp_prove*: -1 = automatic (pageable memory through the prover's pinned staging

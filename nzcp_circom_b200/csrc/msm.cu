@@ -834,6 +834,7 @@ std::atomic<int> g_tune_pair_prefetch[2] = {{0}, {0}};   // forward / backward p
 // profiles/r02_window_rounds_sweep.md) -- the 2 x 1 GB of extra streaming per H MSM and a forward pass that now carries
 // whole points through its registers cost more than the second gather saves.  Kept as an opt-in, off by default.
 std::atomic<int> g_tune_pair_stage{0};
+std::atomic<int> g_tune_sort_threads{1024};
 std::atomic<int> g_tune_gather_hint{0};                  // experiment: .L2::64B fetch-size qualifier on the round-1 gathers
 std::atomic<int> g_tune_acc_prefetch{1};                 // XYZZ accumulate kernel: prefetch the next table point to L1
 
@@ -972,9 +973,14 @@ void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_
     // shared-memory histogram: one block per SM (fewer for small inputs); otherwise 16 global copies of the counters
     uint32_t n_copies = s->n_copies;
     if (s->smem_hist) {
-      uint32_t want = div_up(n_points, kSmemHistThreads);
+      uint32_t want = div_up(n_points, kSmemHistThreads);   // one block per 1024 scalars at most, whatever its thread count
       if (want < n_copies) n_copies = want;
     }
+    // "sort_threads": threads per block of the shared-memory histogram passes (one block per SM, 128 KB of shared memory).
+    // A 1024-thread block needs a whole SM's thread slots and registers at once; a thinner one can be placed beside the
+    // blocks of whatever kernel another stream is running.
+    int sort_threads = g_tune_sort_threads.load();
+    sort_threads = sort_threads >= 1024 ? 1024 : sort_threads >= 512 ? 512 : sort_threads >= 256 ? 256 : 128;
     const uint32_t n_ctr = nb * n_copies;
     // entries index the table of the plan's full point count, so a shorter scalar vector still addresses T[w][i]
     DigitParams dp{n_copies, (uint32_t)n_points, s->table_free ? 0u : (uint32_t)s->n_points, s->c, s->n_windows,
@@ -983,7 +989,7 @@ void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_
     const size_t hist_bytes = (size_t)nb * sizeof(uint32_t);
     if (s->smem_hist) {
       NZCP_CUDA(cudaMemsetAsync(s->counts + n_ctr, 0, sizeof(uint32_t), st));
-      msm_digits_smem_kernel<false><<<n_copies, kSmemHistThreads, hist_bytes, st>>>(scalars, dp, s->counts, nullptr, s->flags);
+      msm_digits_smem_kernel<false><<<n_copies, sort_threads, hist_bytes, st>>>(scalars, dp, s->counts, nullptr, s->flags);
     } else {
       NZCP_CUDA(cudaMemsetAsync(s->counts, 0, (n_ctr + 1) * sizeof(uint32_t), st));
       msm_digits_kernel<false><<<gp, 256, 0, st>>>(scalars, dp, s->counts, nullptr, s->flags);
@@ -1001,7 +1007,7 @@ void msm_sort_launch(MsmSort* s, const Fr* scalars, size_t n_points, cudaStream_
     msm_scan_apply_kernel<<<n_blk, 256, 0, st>>>(s->counts, blk_off, s->offsets, s->smem_hist ? nullptr : s->cursors, n_scan);
     NZCP_LAUNCH_CHECK();
     if (s->smem_hist)
-      msm_digits_smem_kernel<true><<<n_copies, kSmemHistThreads, hist_bytes, st>>>(scalars, dp, s->offsets, s->entries, s->flags);
+      msm_digits_smem_kernel<true><<<n_copies, sort_threads, hist_bytes, st>>>(scalars, dp, s->offsets, s->entries, s->flags);
     else
       msm_digits_kernel<true><<<gp, 256, 0, st>>>(scalars, dp, s->cursors, s->entries, s->flags);
     NZCP_LAUNCH_CHECK();

@@ -6,7 +6,7 @@ namespace nzcp {
 extern std::atomic<int> g_tune_rounds;                                                   // msm.cu
 extern std::atomic<int> g_tune_pair_k[kMsmMaxRounds];
 extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;
-extern std::atomic<int> g_tune_pair_prefetch[2], g_tune_acc_prefetch, g_tune_pair_stage, g_tune_gather_hint;
+extern std::atomic<int> g_tune_pair_prefetch[2], g_tune_acc_prefetch, g_tune_pair_stage, g_tune_gather_hint, g_tune_sort_threads;
 extern std::atomic<int> g_tune_ntt_tma;                                                  // ntt.cu
 extern std::atomic<int> g_tune_c_h, g_tune_c_w;                                          // prover.cu
 extern std::atomic<int> g_tune_stage_mode, g_tune_stage_chunk_kb, g_tune_stage_threads;
@@ -31,6 +31,7 @@ int nzcp_tuning_set(const char* name, int value) {
     else if (k == "acc_prefetch") g_tune_acc_prefetch.store(value);
     else if (k == "pair_stage") g_tune_pair_stage.store(value);
     else if (k == "gather_hint") g_tune_gather_hint.store(value);
+    else if (k == "sort_threads") g_tune_sort_threads.store(value);
     else if (k == "stage_mode") g_tune_stage_mode.store(value);
     else if (k == "stage_chunk_kb") g_tune_stage_chunk_kb.store(value);
     else if (k == "stage_threads") g_tune_stage_threads.store(value);
