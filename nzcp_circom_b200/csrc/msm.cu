@@ -839,12 +839,11 @@ std::atomic<int> g_tune_gather_hint{0};                  // experiment: .L2::64B
 std::atomic<int> g_tune_acc_prefetch{1};                 // XYZZ accumulate kernel: prefetch the next table point to L1
 
 // Pair rounds are OFF for the standalone MSMs unless asked for (nzcp_tuning_set "msm_rounds"); provers turn them on
-// (msm_pick_rounds_prover; "prover_rounds_*" override).  First measurement on the B200, H MSM alone, operand prefetch ON
-// (profiles/r02_pair_rounds.md): they cut the executed products of the H accumulation by a third, but an affine
-// addition needs each operand twice (denominator pass, then the addition itself) and round 1 gathers its operands
-// from the 1 GB window table -- random 128-byte lines come in at ~3.7 TB/s, so round 1 alone costs what the XYZZ kernel
-// needs for the same additions with its single gather hidden under the multiplies (H: 3.1 ms with rounds vs 2.75 ms
-// without; whole-proof throughput +2..3 % at +5 GB of scratch per prover).
+// (msm_pick_rounds_prover; "prover_rounds_*" override).  History of the measurement on the B200 (profiles/r02_pair_rounds.md,
+// r02_window_rounds_sweep.md): with the operands of the next pair prefetched to L1 the H accumulation took 3.1 ms with
+// rounds against 2.75 ms for the XYZZ kernel (an affine addition needs each operand twice, and round 1 gathers them from
+// the 1 GB window table); without that prefetch and with a thread's additions interleaved across its warp it takes
+// 2.58 ms, executes a quarter fewer products, and the whole proof gains 11 %.
 int msm_pick_rounds(size_t n_points, int c) {
   (void)n_points;
   (void)c;
