@@ -210,6 +210,7 @@ int nzcp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
  *   "stage_mode"  host witness upload in nzcp_prove*: -1 = automatic (pageable memory through the prover's pinned staging
  *                 buffer in chunks, caller-pinned memory directly), 0 = always direct, 1 = always staged
  *   "stage_chunk_kb"  staging chunk size in KiB (default 1024)
+ *   "prover_rounds_b2"  pair rounds of the G2 MSM alone (-1 = as the other witness MSMs; another value gives it its own sort)
  *   "prover_c_h" / "prover_c_w"  window bits of the H / witness MSM tables, read by nzcp_zkey_load (0 = default: 16 at 2^20)
  *   "ntt_tma"     1 (default) = TMA-staged low NTT pass (bulk copies + mbarrier, twiddles in shared memory), 0 = thread-loaded
  *   "stage_threads"   host threads sharing the copy into the staging buffer (default 4; 1 = the calling thread alone) */

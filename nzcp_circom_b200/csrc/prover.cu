@@ -23,6 +23,7 @@ thread_local std::atomic<uint64_t>* t_launch_sink = nullptr;
 // Python bytes object) goes through the prover's pinned staging buffer in chunks, so the CPU copy of chunk k+1 overlaps
 // the DMA of chunk k; memory the caller pinned (cudaHostAlloc / cudaHostRegister) is handed to the copy engine directly.
 // 0 = always direct (the driver stages pageable memory itself), 1 = always through the staging buffer.
+std::atomic<int> g_tune_rounds_b2{-1};   // "prover_rounds_b2": pair rounds of the G2 MSM (-1 = as the other witness MSMs)
 std::atomic<int> g_tune_c_h{0}, g_tune_c_w{0};   // "prover_c_h" / "prover_c_w": window bits of the H / witness MSM tables (0 = default)
 std::atomic<int> g_tune_stage_mode{-1};
 std::atomic<int> g_tune_stage_chunk_kb{1024};
@@ -102,6 +103,8 @@ struct nzcp_prover {
   Fr* d_abc = nullptr;
   Fr* d_h = nullptr;
   MsmSort sort_w, sort_h;                       // bucket sorts of the witness and of the h scalars
+  MsmSort sort_b2;                              // the G2 MSM's own witness sort when its round count differs ("prover_rounds_b2")
+  bool own_b2_sort = false;
   MsmRun run_a, run_b1, run_b2, run_c, run_h;
 };
 
@@ -267,6 +270,7 @@ static void prover_release(nzcp_prover* p) {
   msm_run_destroy(&p->run_c);
   msm_run_destroy(&p->run_h);
   msm_sort_destroy(&p->sort_w);
+  msm_sort_destroy(&p->sort_b2);
   msm_sort_destroy(&p->sort_h);
   delete p;
 }
@@ -299,7 +303,16 @@ static nzcp_prover* prover_create_impl(nzcp_zkey* zk, int mode = 0) {
   msm_sort_create(&p->sort_h, n, zk->c_h, rounds_h);
   msm_run_create(&p->run_a, &p->sort_w, false);
   msm_run_create(&p->run_b1, &p->sort_w, false);
-  msm_run_create(&p->run_b2, &p->sort_w, true);
+  // The round plan is part of the sort, so an MSM that wants another number of pair rounds than its siblings needs its
+  // own sort of the same scalars (two more histogram passes over the witness).
+  int rounds_b2 = g_tune_rounds_b2.load();
+  if (rounds_b2 < 0 || rounds_b2 == rounds_w) {
+    msm_run_create(&p->run_b2, &p->sort_w, true);
+  } else {
+    msm_sort_create(&p->sort_b2, zk->n_vars, zk->c_w, rounds_b2);
+    p->own_b2_sort = true;
+    msm_run_create(&p->run_b2, &p->sort_b2, true);
+  }
   msm_run_create(&p->run_c, &p->sort_w, false);
   msm_run_create(&p->run_h, &p->sort_h, false);
   return p.release();
@@ -421,15 +434,21 @@ static void prove_impl(nzcp_prover* p, const uint8_t* h_witness, const Fr* d_wit
   // B2 (G2, the longest) is sorted for on its own stream and launched first.
   cudaStream_t sw = p->st_msm[2];
   NZCP_CUDA(cudaStreamWaitEvent(sw, p->ev[1], 0));
+  if (p->own_b2_sort) {   // B2 sorts for itself on its stream; the shared sort moves to A's stream
+    msm_sort_launch(&p->sort_b2, d_w, m, sw);
+    sw = p->st_msm[0];
+    NZCP_CUDA(cudaStreamWaitEvent(sw, p->ev[1], 0));
+  }
   msm_sort_launch(&p->sort_w, d_w, m, sw);
   NZCP_CUDA(cudaEventRecord(p->ev[5], sw));
   struct Job { MsmRun* run; const MsmTable* tab; int stream; };
   Job jobs[4] = {{&p->run_b2, &zk->tab_b2, 2}, {&p->run_a, &zk->tab_a, 0}, {&p->run_b1, &zk->tab_b1, 1}, {&p->run_c, &zk->tab_c, 3}};
   for (int k = 0; k < 4; k++) {
     cudaStream_t st = p->st_msm[jobs[k].stream];
-    if (st != sw) NZCP_CUDA(cudaStreamWaitEvent(st, p->ev[5], 0));
+    const bool own = p->own_b2_sort && jobs[k].run == &p->run_b2;
+    if (st != sw && !own) NZCP_CUDA(cudaStreamWaitEvent(st, p->ev[5], 0));
     NZCP_CUDA(cudaEventRecord(p->ev[6 + 2 * jobs[k].stream], st));
-    msm_run_launch(jobs[k].run, &p->sort_w, jobs[k].tab, st);
+    msm_run_launch(jobs[k].run, own ? &p->sort_b2 : &p->sort_w, jobs[k].tab, st);
     NZCP_CUDA(cudaEventRecord(p->ev[7 + 2 * jobs[k].stream], st));
   }
   msm_run_launch(&p->run_h, &p->sort_h, &zk->tab_h, sm);

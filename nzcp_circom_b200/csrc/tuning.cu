@@ -8,7 +8,7 @@ extern std::atomic<int> g_tune_pair_k[kMsmMaxRounds];
 extern std::atomic<int> g_tune_rounds_w, g_tune_rounds_h;
 extern std::atomic<int> g_tune_pair_prefetch[2], g_tune_acc_prefetch, g_tune_pair_stage, g_tune_gather_hint, g_tune_sort_threads;
 extern std::atomic<int> g_tune_ntt_tma;                                                  // ntt.cu
-extern std::atomic<int> g_tune_c_h, g_tune_c_w;                                          // prover.cu
+extern std::atomic<int> g_tune_c_h, g_tune_c_w, g_tune_rounds_b2;                        // prover.cu
 extern std::atomic<int> g_tune_stage_mode, g_tune_stage_chunk_kb, g_tune_stage_threads;
 }  // namespace nzcp
 
@@ -36,6 +36,7 @@ int nzcp_tuning_set(const char* name, int value) {
     else if (k == "stage_chunk_kb") g_tune_stage_chunk_kb.store(value);
     else if (k == "stage_threads") g_tune_stage_threads.store(value);
     else if (k == "ntt_tma") g_tune_ntt_tma.store(value);
+    else if (k == "prover_rounds_b2") g_tune_rounds_b2.store(value);
     else if (k == "prover_c_h") g_tune_c_h.store(value);
     else if (k == "prover_c_w") g_tune_c_w.store(value);
     else throw ApiError(NZCP_E_ARG, "unknown tuning knob: " + k);
